@@ -1,0 +1,74 @@
+"""ctypes binding of libgnx.so (include/gnx.h).  There is no CPU fallback: a missing
+library or a missing sm_100 device is an error, raised loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgnx.so")
+_lib = None
+
+c_i64 = C.c_int64
+c_vp = C.c_void_p
+
+
+class GnxError(RuntimeError):
+    pass
+
+
+_SIGS = {
+    "gnx_version": (C.c_int, []),
+    "gnx_last_error": (C.c_char_p, []),
+    "gnx_device_count": (C.c_int, []),
+    "gnx_lr_model_create": (C.c_int, [C.POINTER(c_vp), C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, C.c_int]),
+    "gnx_lr_model_destroy": (None, [c_vp]),
+    "gnx_lr_model_scale": (C.c_int, [c_vp]),
+    "gnx_lr_model_windows": (C.c_int, [c_vp]),
+    "gnx_lr_set_kernel": (C.c_int, [c_vp, C.c_int]),
+    "gnx_lr_predict": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "gnx_lr_predict_f64": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "gnx_gbt_model_create": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gnx_gbt_model_destroy": (None, [c_vp]),
+    "gnx_gbt_smooth": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp]),
+    "gnx_gbt_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "gnx_crf_model_create": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int, c_vp, c_vp]),
+    "gnx_crf_model_destroy": (None, [c_vp]),
+    "gnx_crf_smooth": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp]),
+    "gnx_svc_model_create": (C.c_int, [C.POINTER(c_vp), C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int]),
+    "gnx_svc_model_destroy": (None, [c_vp]),
+    "gnx_svc_predict": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "gnx_svc_kernel_window": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "gnx_gnofix": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "gnx_infer_host": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GnxError(
+                "libgnx.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python -m gnomix_b200.build`. gnomix_b200 has no CPU fallback." % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().gnx_last_error()
+        raise GnxError("%s failed (rc=%d): %s" % (what or "libgnx call", rc, msg.decode() if msg else "?"))
+
+
+def require_gpu():
+    import torch
+    if not torch.cuda.is_available() or lib().gnx_device_count() < 1:
+        raise GnxError("gnomix_b200 needs a B200 (sm_100) GPU; none is visible and there is no CPU fallback")

@@ -1,0 +1,289 @@
+// gbt_smooth.cu -- K4: XGB_Smoother.predict_proba / predict.
+//
+// Replaces slide_window (src/Smooth/utils.py:4-29) + XGBClassifier.predict_proba
+// (src/Smooth/models.py:14-20 via src/Smooth/smooth.py:40-56) + argmax (smooth.py:61).
+// X_slide [N*W, S*A] (150 GB at chr1 x 50k haplotypes) is never built: row (n,w) is
+// the contiguous slice Bpad[n][w*A : w*A + S*A] of the reflect-padded base
+// probabilities of haplotype n, which one CTA keeps in shared memory next to the
+// whole forest.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "gbt_smooth.cuh"
+
+namespace gnx {
+
+__device__ __forceinline__ int spad_to_orig(int j, int W, int pad) {
+    if (j < pad) return pad - 1 - j;
+    if (j >= pad + W) return W - 1 - (j - pad - W);
+    return j - pad;
+}
+
+// margins (float32, tree order, class = t % A) -> xgboost Softmax -> argmax
+template <int AT>
+__device__ __forceinline__ void gbt_finish(const GbtDev& m, float* psum, float* __restrict__ proba_out,
+                                           int32_t* __restrict__ label_out) {
+    const int A = AT ? AT : m.A;
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+    float wmax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++)
+        if (c < A) {
+            psum[c] = GNX_FADD(__ldg(m.base + c), psum[c]);
+            wmax = (c == 0) ? psum[0] : fmaxf(psum[c], wmax);
+        }
+    double wsum = 0.0;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++)
+        if (c < A) {
+            psum[c] = gnx_expf_cr(GNX_FSUB(psum[c], wmax));
+            wsum = GNX_ADD(wsum, (double)psum[c]);
+        }
+    const float ws = (float)wsum;
+    int best = 0;
+    float pbest = 0.f;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++)
+        if (c < A) {
+            const float p = GNX_FDIV(psum[c], ws);
+            if (proba_out) proba_out[c] = p;
+            if (c == 0 || p > pbest) {
+                pbest = p;
+                best = c;
+            }
+        }
+    if (label_out) *label_out = best;
+}
+
+template <int AT>
+__device__ __forceinline__ void gbt_eval_row(const GbtDev& m, const uint2* __restrict__ nodes,
+                                             const float* __restrict__ leaves, const float* __restrict__ row,
+                                             float* psum) {
+    const int A = AT ? AT : m.A;
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+    const int rounds = m.T / A;
+    for (int r = 0; r < rounds; r++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const int t = r * A + c;
+                const uint2* tn = nodes + (size_t)t * m.n_split;
+                int nid = 0;
+                for (int d = 0; d < m.D; d++) {
+                    const uint2 nd = tn[nid];
+                    const float x = row[nd.x & 0x7fffffffu];
+                    const bool left = (x != x) ? (nd.x >> 31) : (x < __uint_as_float(nd.y));
+                    nid = 2 * nid + (left ? 1 : 2);
+                }
+                psum[c] = GNX_FADD(psum[c], leaves[(size_t)t * m.n_leaf + (nid - m.n_split)]);
+            }
+        }
+    }
+}
+
+// One CTA per haplotype (grid-stride).  Shared memory: [forest (optional)] [Bpad row].
+template <int AT, bool FOREST_SMEM>
+__global__ void __launch_bounds__(512, 1)
+gbt_smooth_kernel(GbtDev m, size_t forest_bytes, const float* __restrict__ B, int64_t N, int W,
+                  float* __restrict__ proba, int32_t* __restrict__ label) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int A = AT ? AT : m.A;
+    const uint2* nodes = m.nodes;
+    const float* leaves = m.leaves;
+    float* bp = reinterpret_cast<float*>(smem);
+    if (FOREST_SMEM) {
+        const uint4* src = reinterpret_cast<const uint4*>(m.nodes);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        nodes = reinterpret_cast<const uint2*>(smem);
+        leaves = reinterpret_cast<const float*>(smem + (size_t)m.T * m.n_split * sizeof(uint2));
+        bp = reinterpret_cast<float*>(smem + forest_bytes);
+    }
+    const int pad = (m.S + 1) / 2;
+    const int Wp = W + 2 * pad;
+    for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
+        __syncthreads();
+        const float* bn = B + n * (int64_t)W * A;
+        for (int idx = threadIdx.x; idx < Wp * A; idx += blockDim.x) {
+            const int j = idx / A, a = idx - j * A;
+            bp[idx] = __ldg(bn + (int64_t)spad_to_orig(j, W, pad) * A + a);
+        }
+        __syncthreads();
+        for (int w = threadIdx.x; w < W; w += blockDim.x) {
+            float psum[AT ? AT : GBT_MAX_A];
+            gbt_eval_row<AT>(m, nodes, leaves, bp + (size_t)w * A, psum);
+            gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
+        }
+    }
+}
+
+// smoother.model.predict_proba(rows[k, F]) -- rows straight from global memory
+template <int AT>
+__global__ void gbt_rows_kernel(GbtDev m, const float* __restrict__ rows, int64_t k, float* __restrict__ proba) {
+    const int A = AT ? AT : m.A;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= k) return;
+    float psum[AT ? AT : GBT_MAX_A];
+    gbt_eval_row<AT>(m, m.nodes, m.leaves, rows + r * m.F, psum);
+    gbt_finish<AT>(m, psum, proba + r * A, nullptr);
+}
+
+static void fill_heap(const int32_t* feat, const float* thr, const int32_t* left, const int32_t* right,
+                      const uint8_t* dl, const float* leaf, int node, int h, int depth, int D, uint2* nodes,
+                      float* leaves, int n_split) {
+    if (depth == D) {
+        leaves[h - n_split] = leaf[node];
+        return;
+    }
+    if (feat[node] < 0) {  // leaf above the bottom level: always-left filler, same leaf on both sides
+        float inf = INFINITY;
+        uint32_t bits;
+        memcpy(&bits, &inf, 4);
+        nodes[h] = make_uint2(0x80000000u, bits);
+        fill_heap(feat, thr, left, right, dl, leaf, node, 2 * h + 1, depth + 1, D, nodes, leaves, n_split);
+        fill_heap(feat, thr, left, right, dl, leaf, node, 2 * h + 2, depth + 1, D, nodes, leaves, n_split);
+        return;
+    }
+    uint32_t bits;
+    memcpy(&bits, &thr[node], 4);
+    nodes[h] = make_uint2((uint32_t)feat[node] | ((dl && dl[node]) ? 0x80000000u : 0u), bits);
+    fill_heap(feat, thr, left, right, dl, leaf, left[node], 2 * h + 1, depth + 1, D, nodes, leaves, n_split);
+    fill_heap(feat, thr, left, right, dl, leaf, right[node], 2 * h + 2, depth + 1, D, nodes, leaves, n_split);
+}
+
+static int tree_depth(const int32_t* feat, const int32_t* left, const int32_t* right, int node, int n_nodes, int guard) {
+    if (node < 0 || node >= n_nodes || guard > 64) return -1000;
+    if (feat[node] < 0) return 0;
+    int a = tree_depth(feat, left, right, left[node], n_nodes, guard + 1);
+    int b = tree_depth(feat, left, right, right[node], n_nodes, guard + 1);
+    return 1 + std::max(a, b);
+}
+
+}  // namespace gnx
+
+using namespace gnx;
+
+extern "C" {
+
+int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32_t* feat, const float* thr,
+                         const int32_t* left, const int32_t* right, const uint8_t* default_left,
+                         const float* leaf, const int32_t* tree_offsets, const float* base_margin) {
+    GNX_REQUIRE(out != nullptr, "gnx_gbt_model_create: out is NULL");
+    *out = nullptr;
+    GNX_REQUIRE(A >= 2 && A <= GBT_MAX_A, "gnx_gbt_model_create: A=%d unsupported (2..%d)", A, GBT_MAX_A);
+    GNX_REQUIRE(S >= 1 && (S & 1), "gnx_gbt_model_create: S=%d must be odd and positive", S);
+    GNX_REQUIRE(n_trees > 0 && n_trees % A == 0, "gnx_gbt_model_create: n_trees=%d must be a positive multiple of A=%d", n_trees, A);
+    GNX_REQUIRE(feat && thr && left && right && leaf && tree_offsets && base_margin, "gnx_gbt_model_create: NULL array");
+    if (require_blackwell()) return 1;
+    const int F = S * A;
+    int D = 0;
+    for (int t = 0; t < n_trees; t++) {
+        const int o = tree_offsets[t], nn = tree_offsets[t + 1] - o;
+        GNX_REQUIRE(nn >= 1, "gnx_gbt_model_create: tree %d is empty", t);
+        const int d = tree_depth(feat + o, left + o, right + o, 0, nn, 0);
+        GNX_REQUIRE(d >= 0, "gnx_gbt_model_create: tree %d is malformed", t);
+        D = std::max(D, d);
+        for (int i = 0; i < nn; i++)
+            GNX_REQUIRE(feat[o + i] < F, "gnx_gbt_model_create: tree %d uses feature %d >= S*A=%d", t, feat[o + i], F);
+    }
+    if (D == 0) D = 1;
+    GNX_REQUIRE(D <= GBT_MAX_DEPTH, "gnx_gbt_model_create: depth %d > %d", D, GBT_MAX_DEPTH);
+    const int n_split = (1 << D) - 1, n_leaf = 1 << D;
+    std::vector<uint2> nodes((size_t)n_trees * n_split);
+    std::vector<float> leaves((size_t)n_trees * n_leaf);
+    for (int t = 0; t < n_trees; t++) {
+        const int o = tree_offsets[t];
+        fill_heap(feat + o, thr + o, left + o, right + o, default_left ? default_left + o : nullptr, leaf + o, 0, 0, 0, D,
+                  nodes.data() + (size_t)t * n_split, leaves.data() + (size_t)t * n_leaf, n_split);
+    }
+    const size_t nb = nodes.size() * sizeof(uint2), lb = leaves.size() * sizeof(float);
+    const size_t forest = (nb + lb + 15) & ~size_t(15);
+    char* blob = nullptr;
+    GNX_CUDA(cudaMalloc((void**)&blob, forest + 256));
+    bool ok = cudaMemcpy(blob, nodes.data(), nb, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + nb, leaves.data(), lb, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + forest, base_margin, sizeof(float) * A, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        cudaFree(blob);
+        set_error("gnx_gbt_model_create: H2D copy failed");
+        return 1;
+    }
+    gnx_gbt* m = new gnx_gbt();
+    cudaGetDevice(&m->device);
+    m->d_blob = blob;
+    m->forest_bytes = forest;
+    m->d = GbtDev{A, S, n_trees, D, F, n_split, n_leaf, reinterpret_cast<const uint2*>(blob),
+                  reinterpret_cast<const float*>(blob + nb), reinterpret_cast<const float*>(blob + forest)};
+    *out = m;
+    return 0;
+}
+
+void gnx_gbt_model_destroy(gnx_gbt_t* m) {
+    if (!m) return;
+    if (m->d_blob) cudaFree(m->d_blob);
+    delete m;
+}
+
+#define GBT_DISPATCH_A(A, CALL) \
+    switch (A) {                \
+        case 2: CALL(2); break; \
+        case 3: CALL(3); break; \
+        case 4: CALL(4); break; \
+        case 5: CALL(5); break; \
+        case 6: CALL(6); break; \
+        case 7: CALL(7); break; \
+        case 8: CALL(8); break; \
+        default: CALL(0); break; \
+    }
+
+int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, float* proba_dev, int32_t* label_dev,
+                   void* stream) {
+    GNX_REQUIRE(m != nullptr, "gnx_gbt_smooth: NULL model");
+    GNX_REQUIRE(N >= 0 && W >= 1, "gnx_gbt_smooth: bad shape N=%lld W=%d", (long long)N, W);
+    const int pad = (m->d.S + 1) / 2;
+    GNX_REQUIRE(W >= pad, "gnx_gbt_smooth: W=%d smaller than the reflect pad %d", W, pad);
+    if (N == 0) return 0;
+    GNX_REQUIRE(B_dev && (proba_dev || label_dev), "gnx_gbt_smooth: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bp_bytes = (size_t)(W + 2 * pad) * m->d.A * sizeof(float);
+    const size_t smem_max = 227 * 1024;
+    GNX_REQUIRE(bp_bytes <= smem_max, "gnx_gbt_smooth: W=%d too large for shared memory", W);
+    const bool forest_smem = m->forest_bytes + bp_bytes <= smem_max;
+    const size_t smem = bp_bytes + (forest_smem ? m->forest_bytes : 0);
+    const int grid = (int)std::min<int64_t>(N, (int64_t)sm_count() * (forest_smem ? 1 : 2));
+#define CALL(AT)                                                                                                   \
+    do {                                                                                                           \
+        if (forest_smem) {                                                                                         \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_kernel<AT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_kernel<AT, true><<<grid, 512, smem, st>>>(m->d, m->forest_bytes, B_dev, N, W, proba_dev, label_dev);      \
+        } else {                                                                                                   \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_kernel<AT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_kernel<AT, false><<<grid, 512, smem, st>>>(m->d, m->forest_bytes, B_dev, N, W, proba_dev, label_dev);     \
+        }                                                                                                          \
+    } while (0)
+    GBT_DISPATCH_A(m->d.A, CALL)
+#undef CALL
+    GNX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gnx_gbt_rows(const gnx_gbt_t* m, const float* rows_dev, int64_t k, float* proba_dev, void* stream) {
+    GNX_REQUIRE(m != nullptr, "gnx_gbt_rows: NULL model");
+    GNX_REQUIRE(k >= 0, "gnx_gbt_rows: bad k");
+    if (k == 0) return 0;
+    GNX_REQUIRE(rows_dev && proba_dev, "gnx_gbt_rows: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)ceil_div(k, 128);
+#define CALL(AT) gbt_rows_kernel<AT><<<grid, 128, 0, st>>>(m->d, rows_dev, k, proba_dev)
+    GBT_DISPATCH_A(m->d.A, CALL)
+#undef CALL
+    GNX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+/*
+ * gnx.h -- C ABI of libgnx.so, the B200 (sm_100a) implementation of the gnomix
+ * local-ancestry inference hot path:
+ *
+ *     Base.predict_proba  ->  Smoother.predict_proba / predict  ->  [gnofix]
+ *
+ * Each entry point replaces one call site of the reference (file:line under
+ * AI-sandbox/gnomix @ 43bec05).  The reference is pure Python and has no FFI of its
+ * own; INTEGRATION.md shows the ctypes stub a gnomix maintainer would add at each
+ * site.  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; gnx_last_error()
+ *     returns a thread-local message.  Nothing throws, nothing prints.
+ *   - `*_dev` pointers are device pointers on the CURRENT cuda device and are owned
+ *     by the caller; the library owns only the opaque model handles (which live on
+ *     the device that was current when they were created).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Device-pointer entry points only enqueue work; they do not synchronise.
+ *   - There is NO CPU fallback: without a usable sm_100 device every compute entry
+ *     point fails with an error.
+ *   - Haplotype matrix X: int8, row-major [N, ldX] with ldX >= C, values {0,1,2}
+ *     (2 = missing, src/utils.py:150-153).  Rows 2i, 2i+1 are individual i.
+ *   - Probability tensors: row-major [N, W, A].
+ */
+#ifndef GNX_H_
+#define GNX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNX_VERSION 100 /* 0.1.0 */
+
+typedef struct gnx_lr gnx_lr_t;   /* per-window logistic-regression base (K1) */
+typedef struct gnx_gbt gnx_gbt_t; /* gradient-boosted-tree smoother (K4)      */
+typedef struct gnx_crf gnx_crf_t; /* linear-chain CRF smoother (K5)           */
+typedef struct gnx_svc gnx_svc_t; /* CovRSK string-kernel SVC base (K2+K3)    */
+
+int gnx_version(void);
+const char* gnx_last_error(void);
+/* number of visible CUDA devices with compute capability 10.x; 0 if none */
+int gnx_device_count(void);
+
+/* ---------------------------------------------------------------------------
+ * K1  LogisticRegressionBase.predict_proba for all W windows
+ * replaces: src/Base/base.py:146-180 (Base.predict_proba_vectorized) with the
+ *           per-window models of src/Base/models.py:12-21 (sklearn
+ *           LogisticRegression.predict_proba -> _predict_proba_lr).
+ * coef:      windows concatenated; window w is row-major [A_rows, M_w] float64 with
+ *            M_w = M+2*ctx (w < W-1) or M+2*ctx+rem (w = W-1), feature order = the
+ *            reference's padded window (reflect pad included), A_rows = A (A > 2)
+ *            or 1 (A == 2, sklearn binary layout).
+ * intercept: [W, A_rows] float64.
+ * limbs:     signed base-256 digits per fixed-point weight (0 = default 7).
+ * W is implied: W = C / M.  Output B float32 (or float64) [N, W, A].
+ * ------------------------------------------------------------------------- */
+int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx,
+                        const double* coef, const double* intercept, int limbs);
+void gnx_lr_model_destroy(gnx_lr_t* m);
+/* fixed-point exponent s chosen at create time: q = rint(w * 2^s) */
+int gnx_lr_model_scale(const gnx_lr_t* m);
+int gnx_lr_model_windows(const gnx_lr_t* m);
+/* kernel selector: 0 = tcgen05/TMA/TMEM tensor-core kernel (default),
+ *                  1 = dp4a CUDA-core kernel (cross-check; same exact integer math) */
+int gnx_lr_set_kernel(gnx_lr_t* m, int which);
+int gnx_lr_predict(const gnx_lr_t* m, const int8_t* X_dev, int64_t N, int64_t ldX,
+                   float* B_dev, void* stream);
+int gnx_lr_predict_f64(const gnx_lr_t* m, const int8_t* X_dev, int64_t N, int64_t ldX,
+                       double* B_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K4  XGB_Smoother: slide_window + XGBClassifier.predict_proba + argmax
+ * replaces: src/Smooth/utils.py:4-29 (slide_window), src/Smooth/smooth.py:40-65
+ *           (Smoother.predict_proba / predict) with the model of
+ *           src/Smooth/models.py:14-20 (xgboost multi:softprob).
+ * Forest layout (xgboost dump order): node arrays concatenated over trees, tree t
+ * owns nodes [tree_offsets[t], tree_offsets[t+1]); left/right are node indices
+ * relative to the tree's first node; feat < 0 marks a leaf whose value is leaf[];
+ * split test `x[feat] < thr` -> left, NaN -> default_left; tree t adds to class
+ * t % A; margin_c = base_margin[c] + sum (float32, tree order); softmax float32.
+ * Feature f of row (n,w) is Bpad[n, w + f / A, f % A], Bpad = reflect pad (S+1)/2.
+ * ------------------------------------------------------------------------- */
+int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32_t* feat,
+                         const float* thr, const int32_t* left, const int32_t* right,
+                         const uint8_t* default_left, const float* leaf,
+                         const int32_t* tree_offsets, const float* base_margin);
+void gnx_gbt_model_destroy(gnx_gbt_t* m);
+/* proba_dev [N,W,A] float32 and label_dev [N,W] int32; either may be NULL */
+int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, float* proba_dev,
+                   int32_t* label_dev, void* stream);
+/* smoother.model.predict_proba(rows[k, S*A]) as gnofix calls it
+ * (src/Gnofix/gnofix.py:157): rows are already-flattened scopes, no sliding. */
+int gnx_gbt_rows(const gnx_gbt_t* m, const float* rows_dev, int64_t k, float* proba_dev,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K5  CRF_Smoother.predict_proba (CRF.predict_marginals) + argmax
+ * replaces: src/Smooth/crf.py:62-67 via src/Smooth/smooth.py:40-65.
+ * state_w [A, L] (attribute a -> label y), trans_w [L, L] (i -> j), float64.
+ * ------------------------------------------------------------------------- */
+int gnx_crf_model_create(gnx_crf_t** out, int A, int L, const double* state_w,
+                         const double* trans_w);
+void gnx_crf_model_destroy(gnx_crf_t* m);
+int gnx_crf_smooth(const gnx_crf_t* m, const double* B_dev, int64_t N, int W, double* proba_dev,
+                   int32_t* label_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K2+K3  CovRSKBase.predict_proba: string kernel against the training matrix of
+ * every window + libsvm probability epilogue.
+ * replaces: src/Base/string_kernel.py:91-123 and sklearn.svm.SVC.predict_proba as
+ *           configured at src/Base/models.py:195-215, driven by base.py:146-180.
+ * sv:        support vectors of all windows concatenated; window w holds
+ *            nsv_total[w] rows of M_w int8 features (padded-window feature order),
+ *            grouped by class with n_support[w*A + c] rows for class c.
+ * dual_coef: per window [A-1, nsv_total[w]] float64 (SVC._dual_coef_), concatenated.
+ * intercept, probA, probB: [W, A*(A-1)/2] float64 (SVC._intercept_, probA_, probB_).
+ * Ms:        CovSample(M_w, 0.6, 1.0, seed=37) prefix-stable list, length n_ms.
+ * ------------------------------------------------------------------------- */
+int gnx_svc_model_create(gnx_svc_t** out, int A, int64_t C, int64_t M, int64_t ctx,
+                         const int8_t* sv, const int32_t* n_support, const double* dual_coef,
+                         const double* intercept, const double* probA, const double* probB,
+                         const int32_t* Ms, int n_ms);
+void gnx_svc_model_destroy(gnx_svc_t* m);
+int gnx_svc_predict(const gnx_svc_t* m, const int8_t* X_dev, int64_t N, int64_t ldX,
+                    double* B_dev, void* stream);
+/* raw kernel values of window w against its support vectors: K [N, nsv_total[w]] int32 */
+int gnx_svc_kernel_window(const gnx_svc_t* m, int w, const int8_t* X_dev, int64_t N, int64_t ldX,
+                          int32_t* K_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K6  Gnomix.phase / gnofix with the reference's default arguments
+ * replaces: src/model.py:188-214 and src/Gnofix/gnofix.py:58-208 (+ phasing.py:
+ *           182-198) for all individuals in one launch.
+ * X_dev [2n, ldX] int8 and B_dev [2n, W, A] float32 are updated IN PLACE (tails
+ * swapped); Y_dev [2n, W] int32 receives the final labels; tracker_dev [2n, W]
+ * int32 (nullable) the gnofix_tracker rows.
+ * ------------------------------------------------------------------------- */
+int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float* B_dev,
+               int64_t n_ind, int W, int max_it, int32_t* Y_dev, int32_t* tracker_dev,
+               void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Host-buffer pipeline: Gnomix.predict_proba / predict on a numpy-style host
+ * matrix (src/model.py:169-179, gnomix.py:55-58).  Streams haplotype chunks
+ * through pinned staging buffers (H2D, K1, K4, D2H overlapped on two streams).
+ * X_host may be pageable or pinned.  proba_host [N,W,A] float32 may be NULL.
+ * Synchronous: returns when label_host / proba_host are complete.
+ * ------------------------------------------------------------------------- */
+int gnx_infer_host(const gnx_lr_t* lr, const gnx_gbt_t* gbt, const int8_t* X_host, int64_t N,
+                   int64_t ldX, float* proba_host, int32_t* label_host, int64_t chunk_haps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNX_H_ */

@@ -1,0 +1,498 @@
+"""NumPy restatement of the gnomix inference hot path (TEST INFRASTRUCTURE ONLY).
+
+Each function cites the reference file:line (under /root/reference) it follows.
+Readable and slow on purpose; `oracle/c_oracle.py` wraps a C version of the same
+algorithms (oracle/gnx_oracle.c) for sizes where Python loops are too slow.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# Row A: windowing  (src/Base/base.py:41-44, 146-180)
+# ----------------------------------------------------------------------------
+
+
+def base_pad(X: np.ndarray, ctx: int) -> np.ndarray:
+    """Base.pad, src/Base/base.py:41-44 (reflect including the edge element)."""
+    if ctx == 0:
+        return X
+    pad_left = np.flip(X[:, 0:ctx], axis=1)
+    pad_right = np.flip(X[:, -ctx:], axis=1)
+    return np.concatenate([pad_left, X, pad_right], axis=1)
+
+
+def base_window_ranges(C: int, M: int, ctx: int):
+    """Padded-coordinate [lo, hi) of every base window.
+
+    src/Base/base.py:157-164: windows 0..W-2 are `sliding_window_view(Xpad, M_)`
+    at offsets arange(0,C,M)[:-2]; the last window is Xpad[:, -(M_+rem):].
+    """
+    W = C // M
+    rem = C - M * W
+    M_ = M + 2 * ctx
+    out = [(w * M, w * M + M_) for w in range(W - 1)]
+    out.append((C + 2 * ctx - (M_ + rem), C + 2 * ctx))
+    return out
+
+
+def padded_to_orig(p: np.ndarray, C: int, ctx: int) -> np.ndarray:
+    """Index map of Base.pad: padded column p -> original SNP column."""
+    p = np.asarray(p)
+    return np.where(p < ctx, ctx - 1 - p, np.where(p >= ctx + C, 2 * C + ctx - 1 - p, p - ctx))
+
+
+# ----------------------------------------------------------------------------
+# Row B: logistic-regression base  (src/Base/models.py:12-21 -> sklearn
+# LinearClassifierMixin._predict_proba_lr; OneVsRestClassifier.predict_proba)
+# ----------------------------------------------------------------------------
+
+
+def expit(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def lr_window_proba(Xw: np.ndarray, coef: np.ndarray, intercept: np.ndarray) -> np.ndarray:
+    """One window: decision = Xw(float64) @ coef.T + intercept; expit; row-normalise.
+    coef is [A, M_w] (or [1, M_w] for the binary case), float64."""
+    d = Xw.astype(np.float64) @ coef.T + intercept
+    p = expit(d)
+    if p.shape[1] == 1:
+        return np.concatenate([1.0 - p, p], axis=1)
+    p /= p.sum(axis=1).reshape((p.shape[0], -1))
+    return p
+
+
+def lr_base_predict_proba(X: np.ndarray, coefs, intercepts, C: int, M: int, ctx: int) -> np.ndarray:
+    """Base.predict_proba_vectorized (src/Base/base.py:146-180) with LR windows.
+    Returns float64 [N, W, A]."""
+    Xp = base_pad(X, ctx)
+    out = []
+    for (lo, hi), cf, b in zip(base_window_ranges(C, M, ctx), coefs, intercepts):
+        out.append(lr_window_proba(Xp[:, lo:hi], cf, b))
+    return np.swapaxes(np.array(out), 0, 1)
+
+
+# -- fixed-point form of row B (what the CUDA kernel evaluates exactly) ------
+
+
+def lr_fold_ranges(C: int, M: int, ctx: int):
+    """Original-coordinate SNP range [s_w, e_w) that window w reads after the
+    reflect pads are folded onto the SNPs they mirror."""
+    W = C // M
+    rng = []
+    for w in range(W):
+        s = max(0, w * M - ctx)
+        e = C if w == W - 1 else min(C, w * M + M + ctx)
+        rng.append((s, e))
+    return rng
+
+
+def lr_choose_scale(coefs, C: int, M: int, ctx: int, limbs: int) -> int:
+    """Fixed-point exponent s: q = rint(w * 2^s).  Largest s such that every folded
+    |q| < 2^(8*limbs-2) and 2*sum|q| < 2^62 for every (window, class)."""
+    amax = 0.0
+    ssum = 0.0
+    pr = base_window_ranges(C, M, ctx)
+    fr = lr_fold_ranges(C, M, ctx)
+    for (lo, hi), (s0, e0), cf in zip(pr, fr, coefs):
+        orig = padded_to_orig(np.arange(lo, hi), C, ctx)
+        for a in range(cf.shape[0]):
+            f = np.zeros(e0 - s0)
+            np.add.at(f, orig - s0, cf[a])
+            amax = max(amax, float(np.abs(f).max()))
+            ssum = max(ssum, float(np.abs(f).sum()))
+    if amax == 0.0:
+        return 8 * limbs - 2
+    e1 = int(np.frexp(amax)[1])
+    e2 = int(np.frexp(ssum)[1])
+    return int(min(8 * limbs - 2 - e1, 60 - e2))
+
+
+def lr_quantize_fold(coefs, C: int, M: int, ctx: int, s: int):
+    """Per window: int64 [A_rows, e_w - s_w] = sum of rint(w*2^s) over the padded
+    columns that map to each original SNP (quantise first, fold in integers)."""
+    pr = base_window_ranges(C, M, ctx)
+    fr = lr_fold_ranges(C, M, ctx)
+    out = []
+    for (lo, hi), (s0, e0), cf in zip(pr, fr, coefs):
+        orig = padded_to_orig(np.arange(lo, hi), C, ctx)
+        q = np.rint(np.asarray(cf, dtype=np.float64) * (2.0 ** s)).astype(np.int64)
+        f = np.zeros((cf.shape[0], e0 - s0), dtype=np.int64)
+        for a in range(cf.shape[0]):
+            np.add.at(f[a], orig - s0, q[a])
+        out.append(f)
+    return out
+
+
+def lr_fixed_logits(X: np.ndarray, qfold, intercepts, C: int, M: int, ctx: int, s: int) -> np.ndarray:
+    """Exact integer dot products -> float64 logits [N, W, A_rows]."""
+    fr = lr_fold_ranges(C, M, ctx)
+    N = X.shape[0]
+    out = np.zeros((N, len(fr), qfold[0].shape[0]))
+    for w, ((s0, e0), q) in enumerate(zip(fr, qfold)):
+        tot = X[:, s0:e0].astype(np.int64) @ q.T  # exact (int64)
+        out[:, w, :] = tot.astype(np.float64) * (2.0 ** -s) + intercepts[w]
+    return out
+
+
+# ----------------------------------------------------------------------------
+# Row D: slide_window  (src/Smooth/utils.py:4-29)
+# ----------------------------------------------------------------------------
+
+
+def smooth_pad(B: np.ndarray, S: int) -> np.ndarray:
+    pad = (S + 1) // 2
+    pad_left = np.flip(B[:, 0:pad, :], axis=1)
+    pad_right = np.flip(B[:, -pad:, :], axis=1)
+    return np.concatenate([pad_left, B, pad_right], axis=1)
+
+
+def slide_window(B: np.ndarray, S: int) -> np.ndarray:
+    """float32 [N*W, S*A]; row (n,w) = B_padded[n, w:w+S, :].ravel()."""
+    N, W, A = B.shape
+    Bp = smooth_pad(B, S)
+    out = np.zeros((N, W, A * S), dtype="float32")
+    for n in range(N):
+        for w in range(W):
+            out[n, w, :] = Bp[n, w:w + S].ravel()
+    return out.reshape(N * W, A * S)
+
+
+# ----------------------------------------------------------------------------
+# Row E: gradient-boosted-tree smoother with xgboost multi:softprob semantics
+# (src/Smooth/models.py:14-20, src/Smooth/smooth.py:40-65).  xgboost is absent
+# from /root/reference (requirements.txt:11 pins xgboost==1.1.1); this restates
+# its published CPU predictor: per class psum (float32, tree-index order, tree t
+# belongs to class t % A) + base margin, then common/math.h::Softmax.
+# ----------------------------------------------------------------------------
+
+
+class GBTModel:
+    """Flat xgboost-style forest.  Node arrays are concatenated over trees;
+    tree t owns nodes tree_offsets[t]:tree_offsets[t+1]; child indices are
+    relative to the tree's first node; feat < 0 marks a leaf."""
+
+    def __init__(self, A, n_features, feat, thr, left, right, default_left, leaf, tree_offsets, base_margin):
+        self.A = int(A)
+        self.n_features = int(n_features)
+        self.feat = np.ascontiguousarray(feat, dtype=np.int32)
+        self.thr = np.ascontiguousarray(thr, dtype=np.float32)
+        self.left = np.ascontiguousarray(left, dtype=np.int32)
+        self.right = np.ascontiguousarray(right, dtype=np.int32)
+        self.default_left = np.ascontiguousarray(default_left, dtype=np.uint8)
+        self.leaf = np.ascontiguousarray(leaf, dtype=np.float32)
+        self.tree_offsets = np.ascontiguousarray(tree_offsets, dtype=np.int32)
+        self.base_margin = np.ascontiguousarray(base_margin, dtype=np.float32)
+
+    @property
+    def n_trees(self):
+        return len(self.tree_offsets) - 1
+
+    def max_depth(self):
+        dmax = 0
+        for t in range(self.n_trees):
+            o = self.tree_offsets[t]
+            stack = [(0, 0)]
+            while stack:
+                nid, d = stack.pop()
+                if self.feat[o + nid] < 0:
+                    dmax = max(dmax, d)
+                else:
+                    stack.append((self.left[o + nid], d + 1))
+                    stack.append((self.right[o + nid], d + 1))
+        return dmax
+
+
+def expf_cr(x: np.ndarray) -> np.ndarray:
+    """float32 exp rounded once from float64 (see include/gnx_math.h gnx_expf_cr;
+    the C oracle and the kernels use the bit-reproducible gnx_exp)."""
+    return np.exp(x.astype(np.float64)).astype(np.float32)
+
+
+def gbt_margins(model: GBTModel, rows: np.ndarray) -> np.ndarray:
+    rows = np.asarray(rows, dtype=np.float32)
+    k = rows.shape[0]
+    psum = np.zeros((k, model.A), dtype=np.float32)
+    for t in range(model.n_trees):
+        o = model.tree_offsets[t]
+        nid = np.zeros(k, dtype=np.int64)
+        active = model.feat[o + nid] >= 0
+        while active.any():
+            idx = o + nid[active]
+            x = rows[np.nonzero(active)[0], model.feat[idx]]
+            go_left = np.where(np.isnan(x), model.default_left[idx] != 0, x < model.thr[idx])
+            nid[active] = np.where(go_left, model.left[idx], model.right[idx])
+            active = model.feat[o + nid] >= 0
+        psum[:, t % model.A] = psum[:, t % model.A] + model.leaf[o + nid]
+    return (model.base_margin[None, :] + psum).astype(np.float32)
+
+
+def softmax_xgb(m: np.ndarray) -> np.ndarray:
+    m = np.asarray(m, dtype=np.float32)
+    wmax = m.max(axis=1, keepdims=True)
+    e = expf_cr((m - wmax).astype(np.float32))
+    wsum = np.zeros(len(m), dtype=np.float64)
+    for c in range(m.shape[1]):
+        wsum = wsum + e[:, c].astype(np.float64)
+    return (e / wsum.astype(np.float32)[:, None]).astype(np.float32)
+
+
+def gbt_predict_proba(model: GBTModel, rows: np.ndarray) -> np.ndarray:
+    return softmax_xgb(gbt_margins(model, rows))
+
+
+def xgb_smooth(model: GBTModel, B: np.ndarray, S: int):
+    """Smoother.predict_proba + predict (src/Smooth/smooth.py:40-65)."""
+    N, W, A = B.shape
+    proba = gbt_predict_proba(model, slide_window(B, S)).reshape(-1, W, A)
+    return proba, np.argmax(proba, axis=-1)
+
+
+# ----------------------------------------------------------------------------
+# Row F: linear-chain CRF marginals (src/Smooth/crf.py:62-67 ->
+# sklearn_crfsuite.CRF.predict_marginals -> CRFsuite crf1d_context.c
+# crf1dc_alpha_score / crf1dc_beta_score / crf1dc_marginal_point).
+# sklearn-crfsuite==0.3.6 is absent from /root/reference; restated from the
+# published algorithm.  state_w[a, y]: weight of attribute a for label y;
+# trans_w[i, j]: weight of transition i -> j.
+# ----------------------------------------------------------------------------
+
+
+def crf_marginals(Bn: np.ndarray, state_w: np.ndarray, trans_w: np.ndarray) -> np.ndarray:
+    """One sequence Bn [W, A] (float64) -> marginals [W, L] float64."""
+    T, A = Bn.shape
+    L = state_w.shape[1]
+    state = np.zeros((T, L))
+    for a in range(A):  # items iterate attributes in insertion order "0","1",...
+        state += Bn[:, a:a + 1] * state_w[a][None, :]
+    es = np.exp(state)
+    et = np.exp(trans_w)
+    alpha = np.zeros((T, L))
+    beta = np.zeros((T, L))
+    scale = np.zeros(T)
+    cur = es[0].copy()
+    ssum = 0.0
+    for v in cur:
+        ssum += v
+    scale[0] = 1.0 / ssum if ssum != 0.0 else 1.0
+    alpha[0] = cur * scale[0]
+    for t in range(1, T):
+        cur = np.zeros(L)
+        for i in range(L):
+            cur += alpha[t - 1, i] * et[i]
+        cur *= es[t]
+        ssum = 0.0
+        for v in cur:
+            ssum += v
+        scale[t] = 1.0 / ssum if ssum != 0.0 else 1.0
+        alpha[t] = cur * scale[t]
+    beta[T - 1] = scale[T - 1]
+    for t in range(T - 2, -1, -1):
+        row = beta[t + 1] * es[t + 1]
+        cur = np.zeros(L)
+        for i in range(L):
+            acc = 0.0
+            for j in range(L):
+                acc += et[i, j] * row[j]
+            cur[i] = acc
+        beta[t] = cur * scale[t]
+    return alpha * beta / scale[:, None]
+
+
+def crf_smooth(B: np.ndarray, state_w, trans_w):
+    proba = np.array([crf_marginals(np.asarray(b, dtype=np.float64), state_w, trans_w) for b in B])
+    return proba, np.argmax(proba, axis=-1)
+
+
+def crf_bruteforce_marginals(Bn, state_w, trans_w):
+    """Enumerate all L^T label paths (tiny T only) -- independent pin for crf_marginals."""
+    import itertools
+    T, A = Bn.shape
+    L = state_w.shape[1]
+    state = Bn @ state_w
+    marg = np.zeros((T, L))
+    Z = 0.0
+    for path in itertools.product(range(L), repeat=T):
+        sc = sum(state[t, y] for t, y in enumerate(path))
+        sc += sum(trans_w[path[t], path[t + 1]] for t in range(T - 1))
+        p = np.exp(sc)
+        Z += p
+        for t, y in enumerate(path):
+            marg[t, y] += p
+    return marg / Z
+
+
+# ----------------------------------------------------------------------------
+# Row C: CovRSK string kernel + libsvm probability
+# (src/Base/string_kernel.py:75-123, src/Base/models.py:195-215)
+# ----------------------------------------------------------------------------
+
+
+def cov_sample(M: int, alpha: float = 0.6, beta: float = 1.0, seed: int = 37):
+    """CovSample, src/Base/string_kernel.py:80-89 (consumes the legacy global RNG
+    stream the same way: one np.random.rand() per m)."""
+    rs = np.random.RandomState(seed)
+    u = rs.rand(max(M - 1, 0))
+    Ms = [1]
+    for i, m in enumerate(range(2, M + 1)):
+        if (1 - (alpha ** (m - Ms[-1] + 1))) * (m ** (-beta)) >= u[i]:
+            Ms.append(m)
+    return Ms
+
+
+def covrsk_closed_form(x: np.ndarray, Y: np.ndarray, Ms) -> np.ndarray:
+    """K(x,y) = sum over maximal match runs of length Lr of G(Lr),
+    G(L) = sum_{m in Ms, m<=L} (L-m+1)  (SURVEY.md 8(a) row C closed form of
+    CovRSK_DP_triangular_numbers_vectorized, string_kernel.py:91-101)."""
+    Ms = np.asarray(Ms)
+    Mlen = x.shape[0]
+    G = np.zeros(Mlen + 1, dtype=np.int64)
+    for L in range(1, Mlen + 1):
+        mm = Ms[Ms <= L]
+        G[L] = int((L - mm + 1).sum())
+    out = np.zeros(len(Y), dtype=np.int64)
+    for r, y in enumerate(Y):
+        z = np.concatenate([[0], (x == y).astype(np.int8), [0]])
+        d = np.diff(z)
+        starts = np.nonzero(d == 1)[0]
+        ends = np.nonzero(d == -1)[0]
+        out[r] = int(G[ends - starts].sum())
+    return out
+
+
+def covrsk_kernel(X: np.ndarray, Y: np.ndarray, Ms=None) -> np.ndarray:
+    if Ms is None:
+        Ms = cov_sample(X.shape[1])
+    return np.array([covrsk_closed_form(x, Y, Ms) for x in X])
+
+
+def svc_predict_proba(K: np.ndarray, n_support, dual_coef, intercept, probA, probB) -> np.ndarray:
+    """libsvm svm_predict_probability for a precomputed kernel row block
+    K [n, nSV] (columns already restricted to support vectors, grouped by class).
+    dual_coef = SVC._dual_coef_ [k-1, nSV], intercept = SVC._intercept_.
+    (libsvm svm.cpp sigmoid_predict + multiclass_probability)."""
+    k = len(n_support)
+    start = np.concatenate([[0], np.cumsum(n_support)])[:-1]
+    n = K.shape[0]
+    out = np.zeros((n, k))
+    min_prob = 1e-7
+    for r in range(n):
+        kv = K[r].astype(np.float64)
+        pair = np.zeros((k, k))
+        p = 0
+        for i in range(k):
+            for j in range(i + 1, k):
+                si, sj = start[i], start[j]
+                ci, cj = n_support[i], n_support[j]
+                ssum = 0.0
+                for t in range(ci):
+                    ssum += dual_coef[j - 1, si + t] * kv[si + t]
+                for t in range(cj):
+                    ssum += dual_coef[i, sj + t] * kv[sj + t]
+                dec = ssum + intercept[p]
+                # sklearn negates libsvm's rho into _intercept_ and flips sign conventions for
+                # binary problems only on the public attributes; the underscore ones are libsvm's.
+                fApB = dec * probA[p] + probB[p]
+                if fApB >= 0:
+                    v = np.exp(-fApB) / (1.0 + np.exp(-fApB))
+                else:
+                    v = 1.0 / (1 + np.exp(fApB))
+                v = min(max(v, min_prob), 1 - min_prob)
+                pair[i, j] = v
+                pair[j, i] = 1 - v
+                p += 1
+        if k == 2:
+            out[r] = [pair[0, 1], pair[1, 0]]
+            continue
+        out[r] = multiclass_probability(k, pair)
+    return out
+
+
+def multiclass_probability(k: int, r: np.ndarray) -> np.ndarray:
+    """libsvm multiclass_probability (Wu, Lin, Weng 2004, method 2)."""
+    max_iter = max(100, k)
+    Q = np.zeros((k, k))
+    Qp = np.zeros(k)
+    p = np.full(k, 1.0 / k)
+    eps = 0.005 / k
+    for t in range(k):
+        Q[t, t] = 0.0
+        for j in range(t):
+            Q[t, t] += r[j, t] * r[j, t]
+            Q[t, j] = Q[j, t]
+        for j in range(t + 1, k):
+            Q[t, t] += r[j, t] * r[j, t]
+            Q[t, j] = -r[j, t] * r[t, j]
+    for _ in range(max_iter):
+        pQp = 0.0
+        for t in range(k):
+            Qp[t] = 0.0
+            for j in range(k):
+                Qp[t] += Q[t, j] * p[j]
+            pQp += p[t] * Qp[t]
+        max_error = 0.0
+        for t in range(k):
+            error = abs(Qp[t] - pQp)
+            if error > max_error:
+                max_error = error
+        if max_error < eps:
+            break
+        for t in range(k):
+            diff = (-Qp[t] + pQp) / Q[t, t]
+            p[t] += diff
+            pQp = (pQp + diff * (diff * Q[t, t] + 2 * Qp[t])) / (1 + diff) / (1 + diff)
+            for j in range(k):
+                Qp[j] = (Qp[j] + diff * Q[t, j]) / (1 + diff)
+                p[j] /= (1 + diff)
+    return p
+
+
+# ----------------------------------------------------------------------------
+# Row G: gnofix with the reference's defaults (src/Gnofix/gnofix.py:58-208,
+# src/Gnofix/phasing.py:182-198, called from src/model.py:188-214)
+# ----------------------------------------------------------------------------
+
+
+def gnofix_default(X_m, X_p, B, S, predict_rows, smooth_predict, max_it=50):
+    """gnofix(M,P,B,smoother) with every keyword at its default.
+    predict_rows(rows[k,S*A]) -> proba[k,A]  (smoother.model.predict_proba)
+    smooth_predict(B[2,W,A]) -> labels[2,W]  (smoother.predict)
+    Returns X_m, X_p, Y_m, Y_p, tracker(2,W)."""
+    _, W, A = B.shape
+    window_size = len(X_m) // W
+    X_m = np.array(X_m).astype(int).copy()
+    X_p = np.array(X_p).astype(int).copy()
+    B = np.array(B).copy()
+    Y_m, Y_p = smooth_predict(B).reshape(2, W)
+    half = (S - 1) // 2
+    c_lo, c_hi = half, W - S + half  # centers[0], centers[-1]
+    trk_m, trk_p = np.zeros(W, dtype=int), np.ones(W, dtype=int)
+    X_m_its = []
+    for _ in range(max_it):
+        if any(np.all(X_m == prev) for prev in X_m_its):
+            break
+        X_m_its.append(X_m.copy())
+        for w in range(1, W):
+            if Y_m[w] != Y_m[w - 1] or Y_p[w] != Y_p[w - 1]:
+                center = min(max(w, c_lo), c_hi)
+                lo = center - half
+                m_orig = B[0, lo:lo + S].copy()
+                p_orig = B[1, lo:lo + S].copy()
+                m_sw = np.concatenate([B[0, lo:w], B[1, w:lo + S]])
+                p_sw = np.concatenate([B[1, lo:w], B[0, w:lo + S]])
+                mps = np.array([m_orig, p_orig, m_sw, p_sw])
+                outs = predict_rows(mps.reshape(4, -1)).reshape(-1, 2, A)
+                probs = np.max(np.max(outs, axis=2), axis=1)
+                if probs[1] * 0.5 > probs[0] * (1 - 0.5):
+                    m = np.concatenate([B[0, :w], B[1, w:]])
+                    p = np.concatenate([B[1, :w], B[0, w:]])
+                    B = np.array([m, p])
+                    trk_m, trk_p = (np.concatenate([trk_m[:w], trk_p[w:]]),
+                                    np.concatenate([trk_p[:w], trk_m[w:]]))
+                    i = w * window_size
+                    tmp = X_m.copy()
+                    X_m[i:] = X_p[i:]
+                    X_p[i:] = tmp[i:]
+                    Y_m, Y_p = smooth_predict(B).reshape(2, W)
+    return X_m, X_p, Y_m, Y_p, np.array([trk_m, trk_p])
