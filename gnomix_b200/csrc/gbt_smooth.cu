@@ -122,6 +122,121 @@ gbt_smooth_kernel(GbtDev m, size_t forest_bytes, const float* __restrict__ B, in
     }
 }
 
+
+// ---------------------------------------------------------------- rank-form fast path
+// Depth-4 forests.  Thread = one (haplotype, window) row; all lanes of a warp walk the
+// same tree, so the tree's top three nodes are a broadcast load and every further step
+// is: node word -> (byte offset of the feature in the row, threshold index) -> one
+// integer compare against the pre-ranked input.  Rank rows hold rank << 16, node words
+// are (k << 16 | byte offset), so `x < thr`  <=>  !(rank_word > node_word).
+__device__ __forceinline__ uint32_t gbt_rank_of(const float* __restrict__ tab, int K, float x) {
+    // #{j : tab[j] <= x}
+    int lo = 0, hi = K;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(tab + mid) <= x) lo = mid + 1; else hi = mid;
+    }
+    return (uint32_t)lo;
+}
+
+template <int AT>
+__global__ void __launch_bounds__(RK_THREADS, 1)
+gbt_smooth_rank_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes,
+                       const float* __restrict__ B, int64_t N, int W, int G,
+                       float* __restrict__ proba, int32_t* __restrict__ label) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int A = AT ? AT : m.A;
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(forest_img);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
+    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * RK_LOWER * 4);
+    const uint4* top_s = reinterpret_cast<const uint4*>(smem + (size_t)m.T * (RK_LOWER + RK_LEAVES) * 4);
+    uint32_t* rk = reinterpret_cast<uint32_t*>(smem + forest_bytes);
+    const int pad = (m.S + 1) / 2;
+    const int Wp = W + 2 * pad;
+    const int ast = m.astride;
+    const int hap_words = Wp * ast;
+    int* nan_flag = reinterpret_cast<int*>(rk + (size_t)G * hap_words);
+    const int rounds = m.T / A;
+
+    for (int64_t g0 = (int64_t)blockIdx.x * G; g0 < N; g0 += (int64_t)gridDim.x * G) {
+        const int gn = (int)min((int64_t)G, N - g0);
+        __syncthreads();
+        if (threadIdx.x == 0) *nan_flag = 0;
+        __syncthreads();
+        bool saw_nan = false;
+        for (int idx = threadIdx.x; idx < gn * Wp * A; idx += blockDim.x) {
+            const int h = idx / (Wp * A), rem = idx - h * (Wp * A);
+            const int j = rem / A, a = rem - j * A;
+            const float x = __ldg(B + ((g0 + h) * W + spad_to_orig(j, W, pad)) * A + a);
+            saw_nan |= (x != x);
+            rk[h * hap_words + j * ast + a] = gbt_rank_of(m.thr_table, m.K, x) << 16;
+        }
+        if (saw_nan) *nan_flag = 1;
+        __syncthreads();
+        if (*nan_flag) {
+            // NaN inputs follow each node's default child: generic traversal on float rows
+            __syncthreads();
+            float* bp = reinterpret_cast<float*>(rk);
+            for (int idx = threadIdx.x; idx < gn * Wp * A; idx += blockDim.x) {
+                const int h = idx / (Wp * A), rem = idx - h * (Wp * A);
+                const int j = rem / A, a = rem - j * A;
+                bp[h * hap_words + j * A + a] = __ldg(B + ((g0 + h) * W + spad_to_orig(j, W, pad)) * A + a);
+            }
+            __syncthreads();
+            for (int r = threadIdx.x; r < gn * W; r += blockDim.x) {
+                const int h = r / W, w = r - h * W;
+                const int64_t n = g0 + h;
+                float psum[AMAX];
+                gbt_eval_row<AT>(m, m.nodes, m.leaves, bp + h * hap_words + w * A, psum);
+                gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
+            }
+            continue;
+        }
+        for (int r = threadIdx.x; r < gn * W; r += blockDim.x) {
+            const int h = r / W, w = r - h * W;
+            const int64_t n = g0 + h;
+            const unsigned char* row = reinterpret_cast<const unsigned char*>(rk + h * hap_words + w * ast);
+            float psum[AMAX];
+#pragma unroll
+            for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+            const uint4* tp = top_s;
+            const uint32_t* lw = lower_s;
+            const float* lv = leaves_s;
+#pragma unroll 1
+            for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+                for (int c = 0; c < AMAX; c++) {
+                    if (c < A) {
+                        const uint4 t4 = tp[c];
+                        const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (t4.x & 0xffffu));
+                        const bool b0 = x0 > t4.x;
+                        const uint32_t n1 = b0 ? t4.z : t4.y;
+                        const uint32_t x1 = *reinterpret_cast<const uint32_t*>(row + (n1 & 0xffffu));
+                        const bool b1 = x1 > n1;
+                        const int i2 = (b0 ? 2 : 0) + (b1 ? 1 : 0);
+                        const uint32_t n2 = lw[c * RK_LOWER + i2];
+                        const uint32_t x2 = *reinterpret_cast<const uint32_t*>(row + (n2 & 0xffffu));
+                        const int i3 = 2 * i2 + ((x2 > n2) ? 1 : 0);
+                        const uint32_t n3 = lw[c * RK_LOWER + 4 + i3];
+                        const uint32_t x3 = *reinterpret_cast<const uint32_t*>(row + (n3 & 0xffffu));
+                        const int lf = 2 * i3 + ((x3 > n3) ? 1 : 0);
+                        psum[c] = GNX_FADD(psum[c], lv[c * RK_LEAVES + lf]);
+                    }
+                }
+                tp += A;
+                lw += RK_LOWER * A;
+                lv += RK_LEAVES * A;
+            }
+            gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
+        }
+    }
+}
+
 // smoother.model.predict_proba(rows[k, F]) -- rows straight from global memory
 template <int AT>
 __global__ void gbt_rows_kernel(GbtDev m, const float* __restrict__ rows, int64_t k, float* __restrict__ proba) {
@@ -191,7 +306,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
         for (int i = 0; i < nn; i++)
             GNX_REQUIRE(feat[o + i] < F, "gnx_gbt_model_create: tree %d uses feature %d >= S*A=%d", t, feat[o + i], F);
     }
-    if (D == 0) D = 1;
+    if (D < 4) D = 4;  // shallower forests are padded with always-left fillers (enables the rank-form kernel)
     GNX_REQUIRE(D <= GBT_MAX_DEPTH, "gnx_gbt_model_create: depth %d > %d", D, GBT_MAX_DEPTH);
     const int n_split = (1 << D) - 1, n_leaf = 1 << D;
     std::vector<uint2> nodes((size_t)n_trees * n_split);
@@ -203,11 +318,55 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     }
     const size_t nb = nodes.size() * sizeof(uint2), lb = leaves.size() * sizeof(float);
     const size_t forest = (nb + lb + 15) & ~size_t(15);
+
+    // rank form (see gbt_smooth.cuh): sorted distinct thresholds of the real splits
+    std::vector<float> tab;
+    for (int t = 0; t < n_trees; t++)
+        for (int i = tree_offsets[t]; i < tree_offsets[t + 1]; i++)
+            if (feat[i] >= 0) {
+                GNX_REQUIRE(thr[i] == thr[i], "gnx_gbt_model_create: NaN split threshold in tree %d", t);
+                tab.push_back(thr[i]);
+            }
+    std::sort(tab.begin(), tab.end());
+    tab.erase(std::unique(tab.begin(), tab.end()), tab.end());
+    const int K = (int)tab.size();
+    const int astride = A | 1;
+    const bool rank_ok = (D == 4) && K <= 65535 && (size_t)S * astride * 4 < 65536;
+    std::vector<uint32_t> rimg;  // lower [T][12] | leaves [T][16] | top [T][4]
+    if (rank_ok) {
+        rimg.assign((size_t)n_trees * (RK_LOWER + RK_LEAVES + 4), 0u);
+        uint32_t* lower = rimg.data();
+        float* rleaves = reinterpret_cast<float*>(rimg.data() + (size_t)n_trees * RK_LOWER);
+        uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
+        for (int t = 0; t < n_trees; t++) {
+            for (int h = 0; h < n_split; h++) {
+                const uint2 nd = nodes[(size_t)t * n_split + h];
+                float th;
+                memcpy(&th, &nd.y, 4);
+                const uint32_t f = nd.x & 0x7fffffffu;
+                uint32_t k;
+                if (th == INFINITY && (nd.x >> 31) && f == 0 && !std::binary_search(tab.begin(), tab.end(), th))
+                    k = 0xFFFFu;  // always-left filler
+                else if (th == INFINITY && !std::binary_search(tab.begin(), tab.end(), th))
+                    k = 0xFFFFu;
+                else
+                    k = (uint32_t)(std::lower_bound(tab.begin(), tab.end(), th) - tab.begin());
+                const uint32_t off = ((f / A) * astride + (f % A)) * 4u;
+                const uint32_t word = (k << 16) | off;
+                if (h < 3) top[(size_t)t * 4 + h] = word;
+                else lower[(size_t)t * RK_LOWER + (h - 3)] = word;
+            }
+            memcpy(rleaves + (size_t)t * RK_LEAVES, leaves.data() + (size_t)t * n_leaf, sizeof(float) * RK_LEAVES);
+        }
+    }
+    const size_t rb = rimg.size() * 4, tb = ((size_t)K * 4 + 15) & ~size_t(15);
     char* blob = nullptr;
-    GNX_CUDA(cudaMalloc((void**)&blob, forest + 256));
+    GNX_CUDA(cudaMalloc((void**)&blob, forest + 256 + rb + tb + 16));
     bool ok = cudaMemcpy(blob, nodes.data(), nb, cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(blob + nb, leaves.data(), lb, cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(blob + forest, base_margin, sizeof(float) * A, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (rb) ok &= cudaMemcpy(blob + forest + 256, rimg.data(), rb, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (K) ok &= cudaMemcpy(blob + forest + 256 + rb, tab.data(), (size_t)K * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         cudaFree(blob);
         set_error("gnx_gbt_model_create: H2D copy failed");
@@ -218,7 +377,13 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->d_blob = blob;
     m->forest_bytes = forest;
     m->d = GbtDev{A, S, n_trees, D, F, n_split, n_leaf, reinterpret_cast<const uint2*>(blob),
-                  reinterpret_cast<const float*>(blob + nb), reinterpret_cast<const float*>(blob + forest)};
+                  reinterpret_cast<const float*>(blob + nb), reinterpret_cast<const float*>(blob + forest),
+                  rank_ok ? 1 : 0, K, astride, reinterpret_cast<const float*>(blob + forest + 256 + rb),
+                  reinterpret_cast<const uint4*>(blob + forest + 256 + (size_t)n_trees * (RK_LOWER + RK_LEAVES) * 4),
+                  reinterpret_cast<const uint32_t*>(blob + forest + 256)};
+    m->rank_forest_bytes = rb;
+    m->rank_forest = reinterpret_cast<const unsigned char*>(blob + forest + 256);
+    m->use_rank = 1;
     *out = m;
     return 0;
 }
@@ -253,6 +418,32 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     const size_t bp_bytes = (size_t)(W + 2 * pad) * m->d.A * sizeof(float);
     const size_t smem_max = 227 * 1024;
     GNX_REQUIRE(bp_bytes <= smem_max, "gnx_gbt_smooth: W=%d too large for shared memory", W);
+    if (m->d.rank_ok && m->use_rank) {
+        // fast path: groups of G haplotypes per CTA pass, G chosen for the best row/thread fit
+        const size_t hap_bytes = (size_t)(W + 2 * pad) * m->d.astride * 4;
+        int bestG = 0;
+        double best_eff = 0.0;
+        for (int G = 1; G <= 8; G++) {
+            if (m->rank_forest_bytes + (size_t)G * hap_bytes + 16 > smem_max) break;
+            const int64_t rows = (int64_t)G * W;
+            const double eff = (double)rows / (double)(ceil_div(rows, RK_THREADS) * RK_THREADS);
+            if (eff > best_eff + 0.02) { best_eff = eff; bestG = G; }
+        }
+        if (bestG > 0) {
+            const size_t smem = m->rank_forest_bytes + (size_t)bestG * hap_bytes + 16;
+            const int grid = (int)std::min<int64_t>(ceil_div(N, bestG), (int64_t)sm_count());
+#define CALLR(AT)                                                                                                              \
+    do {                                                                                                                       \
+        GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        gbt_smooth_rank_kernel<AT><<<grid, RK_THREADS, smem, st>>>(m->d, m->rank_forest, m->rank_forest_bytes, B_dev, N, W,  \
+                                                                   bestG, proba_dev, label_dev);                              \
+    } while (0)
+            GBT_DISPATCH_A(m->d.A, CALLR)
+#undef CALLR
+            GNX_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     const bool forest_smem = m->forest_bytes + bp_bytes <= smem_max;
     const size_t smem = bp_bytes + (forest_smem ? m->forest_bytes : 0);
     const int grid = (int)std::min<int64_t>(N, (int64_t)sm_count() * (forest_smem ? 1 : 2));
@@ -269,6 +460,13 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     GBT_DISPATCH_A(m->d.A, CALL)
 #undef CALL
     GNX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gnx_gbt_set_kernel(gnx_gbt_t* m, int which) {
+    GNX_REQUIRE(m != nullptr, "gnx_gbt_set_kernel: NULL model");
+    GNX_REQUIRE(which == 0 || which == 1, "gnx_gbt_set_kernel: unknown kernel %d", which);
+    m->use_rank = (which == 0);
     return 0;
 }
 

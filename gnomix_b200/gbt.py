@@ -27,6 +27,7 @@ class GBTForest:
         self.tree_offsets = np.ascontiguousarray(tree_offsets, dtype=np.int32)
         self.base_margin = np.ascontiguousarray(base_margin, dtype=np.float32)
         self.classes_ = np.arange(self.A)
+        self.kernel = 0  # 0 = rank-form kernel when eligible, 1 = generic float traversal
         self._handles = {}
 
     @property
@@ -110,6 +111,7 @@ class GBTForest:
                 p(self.default_left), p(self.leaf), p(self.tree_offsets), p(self.base_margin)), "gnx_gbt_model_create")
             h = _Handle(out, _lib.lib().gnx_gbt_model_destroy)
             self._handles[key] = h
+        _lib.check(_lib.lib().gnx_gbt_set_kernel(h.ptr, int(getattr(self, "kernel", 0))), "gnx_gbt_set_kernel")
         return h.ptr
 
     def predict_proba(self, rows):

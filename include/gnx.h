@@ -86,6 +86,9 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
                          const uint8_t* default_left, const float* leaf,
                          const int32_t* tree_offsets, const float* base_margin);
 void gnx_gbt_model_destroy(gnx_gbt_t* m);
+/* kernel selector: 0 = rank-form kernel (default; depth <= 4 forests, falls back by itself
+ *                      otherwise), 1 = generic float traversal (cross-check; same results) */
+int gnx_gbt_set_kernel(gnx_gbt_t* m, int which);
 /* proba_dev [N,W,A] float32 and label_dev [N,W] int32; either may be NULL */
 int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, float* proba_dev,
                    int32_t* label_dev, void* stream);

@@ -15,6 +15,7 @@ def _smoother(W, A, S, forest):
     return sm
 
 
+@pytest.mark.parametrize("kernel", [0, 1])
 @pytest.mark.parametrize("W,A,S,N,depth", [
     (160, 7, 75, 37, 4),
     (317, 7, 75, 5, 4),
@@ -23,12 +24,15 @@ def _smoother(W, A, S, forest):
     (40, 12, 9, 10, 5),     # A > 8: generic-A kernel
     (64, 2, 31, 9, 2),
 ])
-def test_gbt_smooth_matches_oracle(W, A, S, N, depth):
+def test_gbt_smooth_matches_oracle(W, A, S, N, depth, kernel):
     from gnomix_b200 import GBTForest
     from oracle import c_oracle as co
     rng = np.random.default_rng(W * 31 + A)
     forest = GBTForest.random(rng, A, S, n_rounds=20 if W > 1000 else 100, depth=depth)
+    forest.kernel = kernel
     B = util.smooth_B(rng, N, W, A)
+    if N > 8:
+        B[N // 2, W // 3, 0] = np.nan      # NaN follows the default child (slow path inside the fast kernel)
     sm = _smoother(W, A, S, forest)
     proba = sm.predict_proba(B)
     label = sm.predict(B)
@@ -36,7 +40,26 @@ def test_gbt_smooth_matches_oracle(W, A, S, N, depth):
     assert proba.dtype == np.float32
     assert np.array_equal(proba.view(np.uint32), p_o.view(np.uint32))
     assert np.array_equal(label, l_o)
-    assert np.array_equal(label, np.argmax(proba, axis=-1))
+    assert np.array_equal(label, np.argmax(np.nan_to_num(proba, nan=-1.0), axis=-1))
+
+
+def test_gbt_thresholds_hit_exactly():
+    """Inputs equal to split thresholds (and one ulp either side) take the same branch as the
+    float compare: the rank transform is exact."""
+    from gnomix_b200 import GBTForest
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(2)
+    W, A, S, N = 150, 7, 75, 6
+    forest = GBTForest.random(rng, A, S, n_rounds=100, depth=4)
+    thr = forest.thr[forest.feat >= 0]
+    pick = rng.choice(thr, size=(N, W, A)).astype(np.float32)
+    jitter = rng.integers(-1, 2, size=pick.shape)
+    B = np.where(jitter < 0, np.nextafter(pick, np.float32(-1)), np.where(jitter > 0, np.nextafter(pick, np.float32(2)), pick)).astype(np.float32)
+    sm = _smoother(W, A, S, forest)
+    proba = sm.predict_proba(B)
+    p_o, l_o = co.gbt_smooth(forest, B, S)
+    assert np.array_equal(proba.view(np.uint32), p_o.view(np.uint32))
+    assert np.array_equal(sm.predict(B), l_o)
 
 
 def test_gbt_rows_matches_oracle_and_slide_window():
