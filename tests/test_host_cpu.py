@@ -1,0 +1,161 @@
+"""CPU tests of the host side: C-ABI exports, plugin surface, geometry, pickling, the
+no-CPU-fallback rule and the multi-rank sharding helpers (gloo, world_size 2)."""
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(libgnx):
+    hdr = open(os.path.join(ROOT, "include", "gnx.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gnx_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    from gnomix_b200 import _lib
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (gnx_[a-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    assert libgnx.gnx_version() == 100
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry point must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gnomix_b200 import _lib
+    from tests import util
+    rng = np.random.default_rng(0)
+    coefs, icpts, ctx = util.random_lr(rng, 1000, 100, 3)
+    base = util.make_lr_base(1000, 100, 3, coefs, icpts)
+    with pytest.raises(_lib.GnxError):
+        base.predict_proba(np.zeros((2, 1000), dtype=np.int8))
+    assert _lib.lib().gnx_device_count() == 0
+    import ctypes as C
+    out = C.c_void_p()
+    rc = _lib.lib().gnx_lr_model_create(C.byref(out), 3, 1000, 100, 50, None, None, 0)
+    assert rc != 0 and _lib.lib().gnx_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gnomix_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no reference oracle", ""), os.path.join(dirpath, f)
+
+
+def test_plugin_surface_matches_reference_signatures():
+    import inspect
+    from gnomix_b200 import Gnomix, Base, Smoother, LogisticRegressionBase, XGB_Smoother, CRF_Smoother, CovRSKBase
+    assert list(inspect.signature(Base.__init__).parameters) == [
+        "self", "chm_len", "window_size", "num_ancestry", "missing_encoding", "context", "train_admix", "n_jobs", "seed", "verbose"]
+    assert list(inspect.signature(Smoother.__init__).parameters) == [
+        "self", "n_windows", "num_ancestry", "smooth_window_size", "model", "calibrate", "n_jobs", "seed", "mode_filter", "verbose"]
+    assert list(inspect.signature(Gnomix.__init__).parameters)[:5] == ["self", "C", "M", "A", "S"]
+    for cls, names in ((Base, ["train", "predict_proba", "predict", "evaluate", "pad", "init_base_models"]),
+                       (Smoother, ["train", "predict_proba", "predict", "evaluate", "process_base_proba"]),
+                       (Gnomix, ["train", "predict", "predict_proba", "phase", "save", "write_config", "write_gen_map_df"])):
+        for n in names:
+            assert callable(getattr(cls, n)), (cls, n)
+    m = Gnomix(C=5000, M=200, A=3, S=9)
+    assert m.W == 25 and m.context == 100 and isinstance(m.base, LogisticRegressionBase) and isinstance(m.smooth, XGB_Smoother)
+    assert m.smooth.gnofix is True and m.smooth.S == 9 and len(m.base.models) == 25
+    assert isinstance(Gnomix(C=5000, M=200, A=3, S=9, mode="fast").smooth, CRF_Smoother)
+    assert isinstance(Gnomix(C=5000, M=200, A=3, S=9, mode="best").base, CovRSKBase)
+    assert Smoother(10, 3, smooth_window_size=8).S == 7  # S forced odd (src/Smooth/smooth.py:14)
+
+
+def test_window_geometry_known_answers():
+    """SURVEY.md 8(a) row A probe values for chr22 / M=857."""
+    from gnomix_b200.base import Base
+    from oracle import np_oracle as npo
+    C, M = 317_408, 857
+    b = Base(C, M, 7, context=428)
+    sl = b.window_slices()
+    assert len(sl) == 370 and sl == npo.base_window_ranges(C, M, 428)
+    lo0, hi0 = sl[0]
+    assert npo.padded_to_orig(np.array([lo0, hi0 - 1]), C, 428).tolist() == [427, 1284]
+    lo, hi = sl[-1]
+    assert hi - lo == 2031
+    o = npo.padded_to_orig(np.array([lo, hi - 1]), C, 428)
+    assert o.tolist() == [315_805, 316_980]
+    X = np.arange(20, dtype=np.int8).reshape(1, 20)
+    b2 = Base(20, 6, 2, context=3)
+    assert np.array_equal(b2.pad(X), npo.base_pad(X, 3))
+
+
+def test_model_pickle_roundtrip_drops_device_handles(tmp_path):
+    from gnomix_b200 import Gnomix, GBTForest
+    from tests import util
+    rng = np.random.default_rng(0)
+    C, M, A, S = 3000, 250, 3, 5
+    m = Gnomix(C, M, A, S)
+    coefs, icpts, ctx = util.random_lr(rng, C, M, A)
+    m.base.set_window_weights(coefs, icpts)
+    m.smooth.model = GBTForest.random(rng, A, m.smooth.S, n_rounds=3)
+    m.base._handles["fake"] = object()
+    blob = pickle.dumps(m)
+    m2 = pickle.loads(blob)
+    assert m2.base._handles == {} and m2.smooth.model._handles == {}
+    c1, b1 = m.base.packed_weights()
+    c2, b2 = m2.base.packed_weights()
+    assert np.array_equal(c1, c2) and np.array_equal(b1, b2)
+    assert np.array_equal(m2.smooth.model.thr, m.smooth.model.thr)
+
+
+def test_partition_keeps_individuals_together():
+    from gnomix_b200.parallel import partition
+    for n in (0, 1, 2, 7, 16, 100_000, 99_999):
+        for world in (1, 2, 3, 8):
+            parts = partition(n, world)
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            for (a, b), (c, d) in zip(parts, parts[1:]):
+                assert b == c
+            for a, b in parts:
+                assert b == a or a % 2 == 0
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 2
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from gnomix_b200 import parallel
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[2], rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+N, C, W = 37, 501, 9
+rng = np.random.default_rng(5)
+X = torch.from_numpy(rng.integers(0, 3, size=(N, C), dtype=np.int8))
+mine = parallel.scatter_rows(X if rank == 0 else None, N, C, torch.int8, "cpu")
+lo, hi = parallel.local_rows(N, 2, rank)
+assert mine.shape[0] == hi - lo and torch.equal(mine, X[lo:hi])
+# stand-in for the per-rank hot path: a row-wise function of the shard
+lab = torch.stack([mine[:, w::W].to(torch.int32).sum(1) for w in range(W)], 1)
+full = parallel.gather_rows(lab, N)
+if rank == 0:
+    want = torch.stack([X[:, w::W].to(torch.int32).sum(1) for w in range(W)], 1)
+    assert torch.equal(full, want)
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_scatter_gather_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % ROOT)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ps = [subprocess.Popen([sys.executable, str(script), str(r), str(port)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+          for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in ps]
+    assert all(p.returncode == 0 for p in ps), outs
+    assert "OK" in outs[0]
