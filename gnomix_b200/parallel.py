@@ -13,7 +13,8 @@ import numpy as np
 
 def partition(n_rows: int, world: int):
     """[(row_lo, row_hi)] per rank: contiguous blocks of whole individuals (even row counts,
-    a trailing odd haplotype stays with the last non-empty block), sizes differing by <= 2."""
+    a trailing odd haplotype stays with the last non-empty block), sizes differing by at most one
+    individual."""
     n_ind = (n_rows + 1) // 2
     per, extra = divmod(n_ind, world)
     out, lo = [], 0

@@ -122,7 +122,7 @@ def test_partition_keeps_individuals_together():
             for a, b in parts:
                 assert b == a or a % 2 == 0
             sizes = [b - a for a, b in parts]
-            assert max(sizes) - min(sizes) <= 2
+            assert max(sizes) - min(sizes) <= 3  # one individual + a trailing odd haplotype
 
 
 _WORKER = r'''
