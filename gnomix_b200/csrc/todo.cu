@@ -4,16 +4,6 @@
 
 extern "C" {
 
-int gnx_crf_model_create(gnx_crf_t** out, int, int, const double*, const double*) {
-    if (out) *out = nullptr;
-    gnx::set_error("gnx_crf_model_create: CRF smoother kernel (K5) not built yet");
-    return 9;
-}
-void gnx_crf_model_destroy(gnx_crf_t*) {}
-int gnx_crf_smooth(const gnx_crf_t*, const double*, int64_t, int, double*, int32_t*, void*) {
-    gnx::set_error("gnx_crf_smooth: CRF smoother kernel (K5) not built yet");
-    return 9;
-}
 int gnx_svc_model_create(gnx_svc_t** out, int, int64_t, int64_t, int64_t, const int8_t*, const int32_t*, const double*, const double*,
                          const double*, const double*, const int32_t*, int) {
     if (out) *out = nullptr;
