@@ -1,6 +1,8 @@
 // gbt_smooth.cuh -- model handle of the tree-ensemble smoother (K4), shared with gnofix (K6)
 #pragma once
 
+#include <math.h>
+
 #include "common.cuh"
 
 namespace gnx {
@@ -32,6 +34,142 @@ struct GbtDev {
     const uint4* top;        // [T] .x .y .z = nodes 0,1,2 as (offset << 16 | k), .w unused
     const uint32_t* lower;   // [T][12] nodes 3..14 as (offset << 16 | k)
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int spad_to_orig(int j, int W, int pad) {
+    if (j < pad) return pad - 1 - j;
+    if (j >= pad + W) return W - 1 - (j - pad - W);
+    return j - pad;
+}
+
+// margins (float32, tree order, class = t % A) -> xgboost Softmax -> argmax
+template <int AT>
+__device__ __forceinline__ void gbt_finish(const GbtDev& m, float* psum, float* __restrict__ proba_out,
+                                           int32_t* __restrict__ label_out) {
+    const int A = AT ? AT : m.A;
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+    float wmax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++)
+        if (c < A) {
+            psum[c] = GNX_FADD(__ldg(m.base + c), psum[c]);
+            wmax = (c == 0) ? psum[0] : fmaxf(psum[c], wmax);
+        }
+    double wsum = 0.0;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++)
+        if (c < A) {
+            psum[c] = gnx_expf_cr(GNX_FSUB(psum[c], wmax));
+            wsum = GNX_ADD(wsum, (double)psum[c]);
+        }
+    const float ws = (float)wsum;
+    int best = 0;
+    float pbest = 0.f;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++)
+        if (c < A) {
+            const float p = GNX_FDIV(psum[c], ws);
+            if (proba_out) proba_out[c] = p;
+            if (c == 0 || p > pbest) {
+                pbest = p;
+                best = c;
+            }
+        }
+    if (label_out) *label_out = best;
+}
+
+template <int AT>
+__device__ __forceinline__ void gbt_eval_row(const GbtDev& m, const uint2* __restrict__ nodes,
+                                             const float* __restrict__ leaves, const float* __restrict__ row,
+                                             float* psum) {
+    const int A = AT ? AT : m.A;
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+    const int rounds = m.T / A;
+    for (int r = 0; r < rounds; r++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const int t = r * A + c;
+                const uint2* tn = nodes + (size_t)t * m.n_split;
+                int nid = 0;
+                for (int d = 0; d < m.D; d++) {
+                    const uint2 nd = tn[nid];
+                    const float x = row[nd.x & 0x7fffffffu];
+                    const bool left = (x != x) ? (nd.x >> 31) : (x < __uint_as_float(nd.y));
+                    nid = 2 * nid + (left ? 1 : 2);
+                }
+                psum[c] = GNX_FADD(psum[c], leaves[(size_t)t * m.n_leaf + (nid - m.n_split)]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t gbt_rank_of(const float* __restrict__ tab, int K, float x) {
+    // #{j : tab[j] <= x}
+    int lo = 0, hi = K;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(tab + mid) <= x) lo = mid + 1; else hi = mid;
+    }
+    return (uint32_t)lo;
+}
+
+
+// Rank-form walk of the whole forest for one row (see GbtDev): `row` points at the row's
+// first rank word (rank << 16, byte-addressed); top/lower/leaves are the forest image
+// (shared memory in the kernels).  psum[c] accumulates class c's leaves in tree order.
+template <int AT>
+__device__ __forceinline__ void gbt_rank_walk(int A, const unsigned char* __restrict__ row, const uint4* __restrict__ tp,
+                                              const uint32_t* __restrict__ lw, const float* __restrict__ lv, int rounds,
+                                              float* psum) {
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const uint4 t4 = tp[c];
+                const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (t4.x & 0xffffu));
+                const bool b0 = x0 > t4.x;
+                const uint32_t n1 = b0 ? t4.z : t4.y;
+                const uint32_t x1 = *reinterpret_cast<const uint32_t*>(row + (n1 & 0xffffu));
+                const bool b1 = x1 > n1;
+                const int i2 = (b0 ? 2 : 0) + (b1 ? 1 : 0);
+                const uint32_t n2 = lw[c * RK_LOWER + i2];
+                const uint32_t x2 = *reinterpret_cast<const uint32_t*>(row + (n2 & 0xffffu));
+                const int i3 = 2 * i2 + ((x2 > n2) ? 1 : 0);
+                const uint32_t n3 = lw[c * RK_LOWER + 4 + i3];
+                const uint32_t x3 = *reinterpret_cast<const uint32_t*>(row + (n3 & 0xffffu));
+                const int lf = 2 * i3 + ((x3 > n3) ? 1 : 0);
+                psum[c] = GNX_FADD(psum[c], lv[c * RK_LEAVES + lf]);
+            }
+        }
+        tp += A;
+        lw += RK_LOWER * A;
+        lv += RK_LEAVES * A;
+    }
+}
+
+// One tree of the rank-form forest for one row: returns the leaf value.
+__device__ __forceinline__ float gbt_rank_tree(const unsigned char* __restrict__ row, const uint4 t4,
+                                               const uint32_t* __restrict__ lw, const float* __restrict__ lv) {
+    const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (t4.x & 0xffffu));
+    const bool b0 = x0 > t4.x;
+    const uint32_t n1 = b0 ? t4.z : t4.y;
+    const uint32_t x1 = *reinterpret_cast<const uint32_t*>(row + (n1 & 0xffffu));
+    const int i2 = (b0 ? 2 : 0) + ((x1 > n1) ? 1 : 0);
+    const uint32_t n2 = lw[i2];
+    const uint32_t x2 = *reinterpret_cast<const uint32_t*>(row + (n2 & 0xffffu));
+    const int i3 = 2 * i2 + ((x2 > n2) ? 1 : 0);
+    const uint32_t n3 = lw[4 + i3];
+    const uint32_t x3 = *reinterpret_cast<const uint32_t*>(row + (n3 & 0xffffu));
+    return lv[2 * i3 + ((x3 > n3) ? 1 : 0)];
+}
+#endif  // __CUDACC__
 
 }  // namespace gnx
 

@@ -1,0 +1,387 @@
+// gnofix.cu -- K6: Gnomix.phase / gnofix with the reference's default arguments, all
+// individuals in one launch.
+//
+// Replaces src/model.py:188-214 (Python loop over individuals) and src/Gnofix/gnofix.py:
+// 58-208 (+ track_switch / correct_phase_error, src/Gnofix/phasing.py:182-198) as called
+// there: max_it=50, check_criterion="disc_smooth", max_center_offset=0, non_lin_s=0,
+// prob_comp="max", prior_switch_prob=0.5, padding=True, no naive switch.
+//
+// What the reference does per individual (haplotypes m, p):
+//   Y = smoother.predict(B); repeat up to max_it times, stopping when X_m repeats:
+//     for w = 1..W-1 with a label discontinuity in either haplotype at w:
+//       scope = S windows centred on clamp(w); score the pair as it is and with the tails
+//       swapped at w by smoother.model.predict_proba on the 4 flattened scopes;
+//       score = max over the 2 haplotypes of the max class probability;
+//       if swapped > original (strict): swap the tails of B, of the tracker and of X
+//       (at SNP w * (C // W)) and re-run smoother.predict on the whole pair.
+//
+// How this file does it, with identical results:
+//   * The base probabilities are rank-transformed once (gbt_smooth.cuh: exact) into a
+//     read-only uint16 array; tail swaps are never applied to it.  One bit per window
+//     (the tracker: which original haplotype the current "m" row comes from) is the whole
+//     state: current_B[h][j] = orig_B[h ^ trk[j]][j].  X and the float B are permuted once
+//     at the end by gnofix_apply_kernel.
+//   * A check at w stages the 2S-1 padded window slots around w for both haplotypes in
+//     shared memory; that one stage serves the 4 candidate scopes and, if the switch is
+//     accepted, the re-smoothing.
+//   * Re-smoothing after a switch at w only re-evaluates the rows whose receptive field
+//     straddles w (at most S-1 rows per haplotype); rows entirely inside the swapped tail
+//     exchange their labels, rows entirely before it keep theirs.  Each row's output depends
+//     only on its own S*A inputs, so this equals the reference's full smoother.predict(B).
+//   * "X_m repeats" is decided from the tracker history and a per-window bit saying whether
+//     the two original haplotypes differ anywhere in that window's SNP block
+//     (gnofix_diff_kernel): X_m equals an earlier X_m iff the trackers differ only on
+//     blocks where the originals are identical.
+//   * A team of 256 threads owns one individual; three teams share one CTA and one copy of
+//     the forest in shared memory; teams pull individuals from a global counter.
+#include <algorithm>
+
+#include "gbt_smooth.cuh"
+
+namespace gnx {
+
+constexpr int GF_TEAM = 256;
+constexpr int GF_MAX_IT = 64;
+
+struct GfArgs {
+    const uint16_t* ranks;   // [2n][W][A] rank of the ORIGINAL base probabilities
+    const uint32_t* diff;    // [n][nw] bit j: original haplotypes differ in SNP block j
+    uint32_t* trk_out;       // [n][nw] final tracker bits
+    int32_t* Y;              // [2n][W] in: smoother labels of the original pair; out: final labels
+    int32_t* tracker;        // [2n][W] or NULL
+    int* counter;            // work queue
+    int64_t n_ind;
+    int W, nw, max_it, teams;
+    size_t team_bytes;
+};
+
+__device__ __forceinline__ void team_sync(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(GF_TEAM) : "memory");
+}
+
+template <int AT>
+__global__ void __launch_bounds__(3 * GF_TEAM, 1)
+gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes, GfArgs g) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int A = AT ? AT : m.A;
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(forest_img);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
+    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * RK_LOWER * 4);
+    const uint4* top_s = reinterpret_cast<const uint4*>(smem + (size_t)m.T * (RK_LOWER + RK_LEAVES) * 4);
+
+    const int team = threadIdx.x / GF_TEAM, tid = threadIdx.x % GF_TEAM;
+    const int W = g.W, S = m.S, T = m.T, ast = m.astride, nw = g.nw;
+    const int pad = (S + 1) / 2, half = (S - 1) / 2;
+    const int NB = 2 * S - 1;                 // staged padded slots per haplotype
+    const int rounds = T / A;
+
+    // ---- team-private shared memory ------------------------------------------------
+    unsigned char* tb = smem + forest_bytes + (size_t)team * g.team_bytes;
+    uint32_t* st = reinterpret_cast<uint32_t*>(tb);                 // [2][NB][ast]
+    uint32_t* cand = st + 2 * NB * ast;                              // [2][S][ast]  (switched m, switched p)
+    float* leafbuf = reinterpret_cast<float*>(cand + 2 * S * ast);   // [4][T]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(leafbuf + 4 * T);   // [max_it][nw]
+    uint32_t* trk = hist + (size_t)g.max_it * nw;                    // [nw]
+    uint32_t* dif = trk + nw;                                        // [nw]
+    float* marg = reinterpret_cast<float*>(dif + nw);                // [4][GBT_MAX_A]
+    float* expv = marg + 4 * GBT_MAX_A;                              // [4][GBT_MAX_A]
+    float* pmax = expv + 4 * GBT_MAX_A;                              // [4]
+    int* ctl = reinterpret_cast<int*>(pmax + 4);                     // [0] next individual, [1] found w, [2] flag
+    signed char* Ys = reinterpret_cast<signed char*>(ctl + 4);       // [2][W]
+
+    for (;;) {
+        team_sync(team);
+        if (tid == 0) ctl[0] = atomicAdd(g.counter, 1);
+        team_sync(team);
+        const int64_t ind = ctl[0];
+        if (ind >= g.n_ind) break;
+        const uint16_t* rk0 = g.ranks + (size_t)(2 * ind) * W * A;   // original haplotype 0; haplotype 1 follows
+        for (int i = tid; i < 2 * W; i += GF_TEAM) Ys[i] = (signed char)g.Y[(size_t)(2 * ind) * W + i];
+        for (int i = tid; i < nw; i += GF_TEAM) {
+            trk[i] = 0u;
+            dif[i] = g.diff[(size_t)ind * nw + i];
+        }
+        team_sync(team);
+
+        for (int it = 0; it < g.max_it; it++) {
+            // ---- stop if X_m was seen before (gnofix.py:108-113) ----------------------
+            if (tid == 0) ctl[2] = 0;
+            team_sync(team);
+            if (tid < it) {
+                bool same = true;
+                for (int i = 0; i < nw; i++) same &= (((hist[(size_t)tid * nw + i] ^ trk[i]) & dif[i]) == 0u);
+                if (same) ctl[2] = 1;
+            }
+            team_sync(team);
+            if (ctl[2]) break;
+            for (int i = tid; i < nw; i += GF_TEAM) hist[(size_t)it * nw + i] = trk[i];
+
+            int w_cur = 1;
+            for (;;) {
+                // ---- next w >= w_cur with a discontinuity in either haplotype (gnofix.py:32)
+                int w = W;
+                for (int base = w_cur; base < W; base += GF_TEAM) {
+                    team_sync(team);
+                    if (tid == 0) ctl[1] = W;
+                    team_sync(team);
+                    const int ww = base + tid;
+                    if (ww < W && (Ys[ww] != Ys[ww - 1] || Ys[W + ww] != Ys[W + ww - 1])) atomicMin(&ctl[1], ww);
+                    team_sync(team);
+                    w = ctl[1];
+                    if (w < W) break;
+                }
+                if (w >= W) break;
+                w_cur = w + 1;
+
+                // ---- stage padded slots [jlo, jlo + NB) of the CURRENT pair --------------
+                // rows whose receptive field straddles w (rows < pad also read reflected windows up to pad-1-row)
+                const int r_lo = (w <= pad - 1) ? 0 : w - (S - 1 - pad), r_hi = min(W - 1, w + pad - 1);
+                const int jlo = r_lo;
+                const int nslots = r_hi - r_lo + S;
+                for (int idx = tid; idx < 2 * nslots * A; idx += GF_TEAM) {
+                    const int h = idx / (nslots * A), rem = idx - h * (nslots * A);
+                    const int jj = rem / A, a = rem - jj * A;
+                    const int o = spad_to_orig(jlo + jj, W, pad);
+                    const int src = h ^ ((trk[o >> 5] >> (o & 31)) & 1u);
+                    st[(h * NB + jj) * ast + a] = (uint32_t)__ldg(rk0 + ((size_t)src * W + o) * A + a) << 16;
+                }
+                // scope of the check: S windows centred on clamp(w) (gnofix.py:122-130), in padded slots
+                const int center = min(max(w, half), W - S + half);
+                const int lo = center - half;              // first original window of the scope
+                const int sj = lo + pad - jlo;             // its slot inside the stage
+                team_sync(team);
+                // switched candidates: m' = m[lo:w] ++ p[w:lo+S],  p' = p[lo:w] ++ m[w:lo+S]
+                for (int idx = tid; idx < 2 * S * A; idx += GF_TEAM) {
+                    const int h = idx / (S * A), rem = idx - h * (S * A);
+                    const int s = rem / A, a = rem - s * A;
+                    const int src = (lo + s < w) ? h : (1 - h);
+                    cand[(h * S + s) * ast + a] = st[(src * NB + sj + s) * ast + a];
+                }
+                team_sync(team);
+                // ---- 4 rows x T trees (smoother.model.predict_proba, gnofix.py:157) --------
+                {
+                    const int r = tid >> 6, q = tid & 63;
+                    const unsigned char* row = reinterpret_cast<const unsigned char*>(
+                        r < 2 ? st + (r * NB + sj) * ast : cand + ((r - 2) * S) * ast);
+                    for (int t = q; t < T; t += 64)
+                        leafbuf[r * T + t] = gbt_rank_tree(row, top_s[t], lower_s + t * RK_LOWER, leaves_s + t * RK_LEAVES);
+                }
+                team_sync(team);
+                if (tid < 4 * A) {
+                    const int r = tid / A, c = tid - r * A;
+                    float ps = 0.f;
+                    for (int rd = 0; rd < rounds; rd++) ps = GNX_FADD(ps, leafbuf[r * T + rd * A + c]);
+                    marg[r * GBT_MAX_A + c] = GNX_FADD(__ldg(m.base + c), ps);
+                }
+                team_sync(team);
+                if (tid < 4 * A) {
+                    const int r = tid / A, c = tid - r * A;
+                    float wmax = marg[r * GBT_MAX_A];
+                    for (int k = 1; k < A; k++) wmax = fmaxf(marg[r * GBT_MAX_A + k], wmax);
+                    expv[r * GBT_MAX_A + c] = gnx_expf_cr(GNX_FSUB(marg[r * GBT_MAX_A + c], wmax));
+                }
+                team_sync(team);
+                if (tid < 4) {
+                    double wsum = 0.0;
+                    for (int k = 0; k < A; k++) wsum = GNX_ADD(wsum, (double)expv[tid * GBT_MAX_A + k]);
+                    const float ws = (float)wsum;
+                    float best = 0.f;
+                    for (int k = 0; k < A; k++) {
+                        const float p = GNX_FDIV(expv[tid * GBT_MAX_A + k], ws);
+                        if (k == 0 || p > best) best = p;
+                    }
+                    pmax[tid] = best;
+                }
+                team_sync(team);
+                const float p_orig = fmaxf(pmax[0], pmax[1]), p_sw = fmaxf(pmax[2], pmax[3]);
+                if (!(p_sw > p_orig)) continue;           // gnofix.py:171 (the 0.5 prior cancels)
+
+                // ---- accept: swap tails at w --------------------------------------------
+                for (int i = tid; i < nw; i += GF_TEAM) {
+                    const int b0 = i * 32;
+                    uint32_t mask = 0u;
+                    if (b0 >= w) mask = 0xffffffffu;
+                    else if (b0 + 32 > w) mask = 0xffffffffu << (w - b0);
+                    if (i == nw - 1 && (W & 31)) mask &= (1u << (W & 31)) - 1u;
+                    trk[i] ^= mask;
+                }
+                // rows entirely inside the tail exchange labels; staged slots inside the tail swap
+                for (int ww = w + pad + tid; ww < W; ww += GF_TEAM) {
+                    const signed char a0 = Ys[ww];
+                    Ys[ww] = Ys[W + ww];
+                    Ys[W + ww] = a0;
+                }
+                for (int idx = tid; idx < nslots * A; idx += GF_TEAM) {
+                    const int jj = idx / A, a = idx - jj * A;
+                    if (spad_to_orig(jlo + jj, W, pad) >= w) {
+                        const uint32_t v0 = st[(jj)*ast + a];
+                        st[(jj)*ast + a] = st[(NB + jj) * ast + a];
+                        st[(NB + jj) * ast + a] = v0;
+                    }
+                }
+                team_sync(team);
+                // rows straddling w: re-evaluate (Smoother.predict, smooth.py:58-61)
+                const int nrows = r_hi - r_lo + 1;
+                for (int task = tid; task < 2 * nrows; task += GF_TEAM) {
+                    const int h = task / nrows, rr = task - h * nrows;
+                    const unsigned char* row = reinterpret_cast<const unsigned char*>(st + (h * NB + rr) * ast);
+                    float psum[AMAX];
+                    gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
+                    int32_t lab;
+                    gbt_finish<AT>(m, psum, nullptr, &lab);
+                    Ys[h * W + r_lo + rr] = (signed char)lab;
+                }
+                team_sync(team);
+            }
+        }
+        // ---- results -----------------------------------------------------------------
+        team_sync(team);
+        for (int i = tid; i < 2 * W; i += GF_TEAM) g.Y[(size_t)(2 * ind) * W + i] = Ys[i];
+        for (int i = tid; i < nw; i += GF_TEAM) g.trk_out[(size_t)ind * nw + i] = trk[i];
+        if (g.tracker)
+            for (int i = tid; i < W; i += GF_TEAM) {
+                const int b = (trk[i >> 5] >> (i & 31)) & 1u;
+                g.tracker[(size_t)(2 * ind) * W + i] = b;
+                g.tracker[(size_t)(2 * ind + 1) * W + i] = 1 - b;
+            }
+    }
+}
+
+// rank of every original base probability (exact, see gbt_smooth.cuh); NaN ranks above
+// every threshold.
+__global__ void gnofix_rank_kernel(GbtDev m, const float* __restrict__ B, int64_t count, uint16_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = __ldg(B + i);
+        out[i] = (x != x) ? (uint16_t)m.K : (uint16_t)gbt_rank_of(m.thr_table, m.K, x);
+    }
+}
+
+// diff bit j of individual i: rows 2i and 2i+1 of X differ somewhere in SNP block j
+// (blocks of ws = C / W SNPs, the last block runs to C -- gnofix.py:74, phasing.py:192-196)
+__global__ void gnofix_diff_kernel(const int8_t* __restrict__ X, int64_t ldX, int64_t C, int W, int nw, int64_t ws,
+                                   uint32_t* __restrict__ diff) {
+    const int64_t ind = blockIdx.x;
+    const int8_t* a = X + (2 * ind) * ldX;
+    const int8_t* b = a + ldX;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < W; j += nwarps) {
+        const int64_t s = (int64_t)j * ws, e = (j == W - 1) ? C : s + ws;
+        bool d = false;
+        for (int64_t p = s + lane; p < e; p += 32) d |= (a[p] != b[p]);
+        const unsigned any = __ballot_sync(0xffffffffu, d);
+        if (lane == 0 && any) atomicOr(diff + ind * nw + (j >> 5), 1u << (j & 31));
+    }
+}
+
+// final permutation: X tails (SNP blocks) and float B windows of the two haplotypes
+// exchanged wherever the tracker bit is set
+__global__ void gnofix_apply_kernel(int8_t* __restrict__ X, int64_t ldX, int64_t C, float* __restrict__ B, int W, int A, int nw,
+                                    int64_t ws, const uint32_t* __restrict__ trk) {
+    const int64_t ind = blockIdx.x;
+    int8_t* a = X + (2 * ind) * ldX;
+    int8_t* b = a + ldX;
+    const uint32_t* t = trk + ind * nw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < W; j += nwarps) {
+        if (!((t[j >> 5] >> (j & 31)) & 1u)) continue;
+        if (X) {
+            const int64_t s = (int64_t)j * ws, e = (j == W - 1) ? C : s + ws;
+            for (int64_t p = s + lane; p < e; p += 32) {
+                const int8_t v = a[p];
+                a[p] = b[p];
+                b[p] = v;
+            }
+        }
+        if (B) {
+            float* b0 = B + ((2 * ind) * W + j) * A;
+            float* b1 = B + ((2 * ind + 1) * W + j) * A;
+            if (lane < A) {
+                const float v = b0[lane];
+                b0[lane] = b1[lane];
+                b1[lane] = v;
+            }
+        }
+    }
+}
+
+}  // namespace gnx
+
+using namespace gnx;
+
+extern "C" int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float* B_dev, int64_t n_ind, int W,
+                          int max_it, int32_t* Y_dev, int32_t* tracker_dev, void* stream) {
+    GNX_REQUIRE(m != nullptr, "gnx_gnofix: NULL smoother model");
+    GNX_REQUIRE(n_ind >= 0 && W >= 2 && C >= W && ldX >= C, "gnx_gnofix: bad shape n_ind=%lld W=%d C=%lld ldX=%lld", (long long)n_ind, W,
+                (long long)C, (long long)ldX);
+    GNX_REQUIRE(max_it >= 1 && max_it <= GF_MAX_IT, "gnx_gnofix: max_it=%d outside 1..%d", max_it, GF_MAX_IT);
+    if (n_ind == 0) return 0;
+    GNX_REQUIRE(B_dev && Y_dev, "gnx_gnofix: NULL buffer (X_dev may be NULL to skip the SNP-level swap)");
+    GNX_REQUIRE(m->d.rank_ok, "gnx_gnofix: needs a forest of depth <= 4 with <= 65535 distinct thresholds (the rank-form image)");
+    const int S = m->d.S, A = m->d.A, T = m->d.T;
+    GNX_REQUIRE(W >= 2 * S, "gnx_gnofix: W=%d < 2*S=%d (XGB_Smoother asserts W >= 2S, src/Smooth/models.py:13)", W, 2 * S);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nw = (W + 31) / 32;
+    const int64_t ws = C / W;
+
+    // initial labels of the pair as it is: smoother.predict(B) (gnofix.py:80)
+    if (gnx_gbt_smooth(m, B_dev, 2 * n_ind, W, nullptr, Y_dev, stream)) return 1;
+
+    // scratch: ranks u16 [2n][W][A] | diff [n][nw] | trk [n][nw] | counter
+    const size_t rb = ((size_t)2 * n_ind * W * A * sizeof(uint16_t) + 255) & ~size_t(255);
+    const size_t db = ((size_t)n_ind * nw * 4 + 255) & ~size_t(255);
+    char* scratch = nullptr;
+    GNX_CUDA(cudaMallocAsync((void**)&scratch, rb + 2 * db + 256, st));
+    uint16_t* ranks = reinterpret_cast<uint16_t*>(scratch);
+    uint32_t* diff = reinterpret_cast<uint32_t*>(scratch + rb);
+    uint32_t* trk = reinterpret_cast<uint32_t*>(scratch + rb + db);
+    int* counter = reinterpret_cast<int*>(scratch + rb + 2 * db);
+    GNX_CUDA(cudaMemsetAsync(scratch + rb, 0, 2 * db + 256, st));
+    const int64_t count = 2 * n_ind * W * A;
+    gnofix_rank_kernel<<<(int)std::min<int64_t>(ceil_div(count, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(m->d, B_dev, count, ranks);
+    if (X_dev)
+        gnofix_diff_kernel<<<(unsigned)n_ind, 256, 0, st>>>(X_dev, ldX, C, W, nw, ws, diff);
+    else
+        GNX_CUDA(cudaMemsetAsync(diff, 0xff, db, st));  // no X: treat every block as differing (tracker equality)
+
+    const int NB = 2 * S - 1, ast = m->d.astride;
+    size_t team_bytes = (size_t)2 * NB * ast * 4 + (size_t)2 * S * ast * 4 + (size_t)4 * T * 4 + (size_t)max_it * nw * 4 + (size_t)2 * nw * 4 +
+                        (size_t)(8 * GBT_MAX_A + 4) * 4 + 16 + (size_t)2 * W;
+    team_bytes = (team_bytes + 15) & ~size_t(15);
+    const size_t smem_max = 227 * 1024;
+    int teams = 3;
+    while (teams > 1 && m->rank_forest_bytes + teams * team_bytes > smem_max) teams--;
+    GNX_REQUIRE(m->rank_forest_bytes + teams * team_bytes <= smem_max, "gnx_gnofix: W=%d / forest too large for shared memory", W);
+    const size_t smem = m->rank_forest_bytes + teams * team_bytes;
+    GfArgs g{ranks, diff, trk, Y_dev, tracker_dev, counter, n_ind, W, nw, max_it, teams, team_bytes};
+    const int grid = (int)std::min<int64_t>(ceil_div(n_ind, teams), (int64_t)sm_count());
+#define CALLG(AT)                                                                                                  \
+    do {                                                                                                           \
+        GNX_CUDA(cudaFuncSetAttribute(gnofix_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gnofix_kernel<AT><<<grid, teams * GF_TEAM, smem, st>>>(m->d, m->rank_forest, m->rank_forest_bytes, g);     \
+    } while (0)
+    switch (A) {
+        case 2: CALLG(2); break;
+        case 3: CALLG(3); break;
+        case 4: CALLG(4); break;
+        case 5: CALLG(5); break;
+        case 6: CALLG(6); break;
+        case 7: CALLG(7); break;
+        case 8: CALLG(8); break;
+        default: CALLG(0); break;
+    }
+#undef CALLG
+    GNX_CUDA(cudaGetLastError());
+    if (X_dev)
+        gnofix_apply_kernel<<<(unsigned)n_ind, 256, 0, st>>>(X_dev, ldX, C, B_dev, W, A, nw, ws, trk);
+    else
+        gnofix_apply_kernel<<<(unsigned)n_ind, 256, 0, st>>>(nullptr, 0, 0, B_dev, W, A, nw, 1, trk);
+    GNX_CUDA(cudaGetLastError());
+    GNX_CUDA(cudaFreeAsync(scratch, st));
+    return 0;
+}

@@ -19,8 +19,4 @@ int gnx_svc_kernel_window(const gnx_svc_t*, int, const int8_t*, int64_t, int64_t
     gnx::set_error("gnx_svc_kernel_window: CovRSK kernel (K2) not built yet");
     return 9;
 }
-int gnx_gnofix(const gnx_gbt_t*, int8_t*, int64_t, int64_t, float*, int64_t, int, int, int32_t*, int32_t*, void*) {
-    gnx::set_error("gnx_gnofix: Gnofix kernel (K6) not built yet");
-    return 9;
-}
 }

@@ -7,24 +7,50 @@ import numpy as np
 from . import _lib
 
 
-def phase_all(model, X, B=None, max_it=50, verbose=False):
-    """Gnomix.phase (src/model.py:188-214): returns X_phased [N, C] int, Y_phased [N, W] int."""
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def phase_device(smoother, Xd, ld, C, Bd, max_it=50, want_tracker=False):
+    """In-place on device tensors: Xd int8 [2n, ld] (or None), Bd float32 [2n, W, A].
+    Returns (Y int32 [2n, W], tracker int32 [2n, W] or None)."""
+    import torch
+    n2, W, A = Bd.shape
+    assert n2 % 2 == 0, "gnofix works on haplotype pairs (rows 2i, 2i+1)"
+    Y = torch.empty((n2, W), dtype=torch.int32, device=Bd.device)
+    trk = torch.empty((n2, W), dtype=torch.int32, device=Bd.device) if want_tracker else None
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().gnx_gnofix(smoother.model.handle(smoother.S), Xd.data_ptr() if Xd is not None else None, int(ld), int(C),
+                                     Bd.data_ptr(), n2 // 2, W, int(max_it), Y.data_ptr(),
+                                     trk.data_ptr() if want_tracker else None, st), "gnx_gnofix")
+    return Y, trk
+
+
+def phase_all(model, X, B=None, max_it=50, verbose=False, want_tracker=False):
+    """Gnomix.phase (src/model.py:188-214): returns X_phased [N, C] int, Y_phased [N, W] int
+    (an odd trailing haplotype is dropped, as the reference's N//2 reshape does)."""
     import torch
     from .base import to_device_haplotypes
     _lib.require_gpu()
-    X = np.asarray(X)
+    on_device = _is_torch(X) and X.is_cuda
     N, Cc = X.shape
     n = N // 2
-    W, A = model.W, model.A
-    Xd_view, ld = to_device_haplotypes(X[:2 * n])
-    Xd_view = Xd_view.clone() if Xd_view.data_ptr() % 16 else Xd_view
+    Xv, ld = to_device_haplotypes(X[:2 * n])
+    if on_device and Xv.data_ptr() == X.data_ptr():
+        Xv = Xv.clone()  # the reference returns fresh arrays and leaves its input alone
+        ld = Xv.stride(0)
     if B is None:
-        Bd = model.base._device_predict(Xd_view, ld)
+        Bd = model.base._device_predict(Xv, ld)
+    elif _is_torch(B):
+        Bd = B[:2 * n].to(device="cuda", dtype=torch.float32).clone()
     else:
         Bd = torch.from_numpy(np.ascontiguousarray(np.asarray(B)[:2 * n], dtype=np.float32)).cuda()
-    Y = torch.empty((2 * n, W), dtype=torch.int32, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
-    _lib.check(_lib.lib().gnx_gnofix(model.smooth.model.handle(model.smooth.S), Xd_view.data_ptr(), ld, Cc, Bd.data_ptr(),
-                                     n, W, int(max_it), Y.data_ptr(), None, st), "gnx_gnofix")
-    torch.cuda.current_stream().synchronize()
-    return Xd_view.cpu().numpy().astype(int), Y.cpu().numpy().astype(int)
+    Y, trk = phase_device(model.smooth, Xv, ld, Cc, Bd, max_it=max_it, want_tracker=want_tracker)
+    if on_device:
+        out = (Xv, Y)
+    else:
+        torch.cuda.current_stream().synchronize()
+        out = (Xv.cpu().numpy().astype(int), Y.cpu().numpy().astype(int))
+    if want_tracker:
+        return out + ((trk if on_device else trk.cpu().numpy()),)
+    return out

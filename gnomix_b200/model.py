@@ -142,13 +142,13 @@ class Gnomix:
                 if type(val) in [int, float, str, bool, np.float64, np.float32, np.int64]:
                     f.write("{}\t{}\n".format(attr, val))
 
-    def phase(self, X, B=None, verbose=False):
+    def phase(self, X, B=None, verbose=False, want_tracker=False):
         """Gnofix over all individuals (src/model.py:188-214): one launch instead of a
         Python loop over individuals."""
         assert self.smooth is not None, "Smoother is not trained, returning original haplotypes"
         assert self.smooth.gnofix, "Type of Smoother ({}) does not currently support re-phasing".format(self.smooth)
         from .gnofix import phase_all
-        return phase_all(self, X, B=B, verbose=verbose)
+        return phase_all(self, X, B=B, verbose=verbose, want_tracker=want_tracker)
 
     # -- host-buffer fast path (include/gnx.h gnx_infer_host) ------------------
     def predict_host(self, X, want_proba=False, chunk_haps=0):
