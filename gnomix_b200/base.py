@@ -237,13 +237,134 @@ class LogisticRegressionBase(Base):
 
 
 class CovRSKBase(Base):
-    """src/Base/models.py:195-215 (string-kernel SVC per window)."""
+    """src/Base/models.py:195-215: one SVC(kernel=CovRSK string kernel, probability=True) per
+    window.  Inference runs K2 (bit-plane string kernel against the window's support
+    vectors) + K3 (libsvm probability epilogue) on the GPU.  Training stays on the host
+    (libsvm through scikit-learn, as in the reference) but takes its Gram matrices from K2
+    instead of the reference's Python DP (src/Base/string_kernel.py:91-111)."""
+
+    MS_ALPHA, MS_BETA, MS_SEED = 0.6, 1.0, 37  # CovRSK_DP_triangular_numbers defaults
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.log_inference = True
         self.train_admix = False
-        self.init_base_models(lambda: None)
+        self.models = [None] * self.W
+        self.sv_rows = [None] * self.W      # int8 [nSV_w, M_w]: training rows at support_, grouped by class
 
-    def _device_predict(self, Xd, ld):
-        raise _lib.GnxError("CovRSKBase: the K2/K3 kernels are not built yet")
+    @staticmethod
+    def cov_sample(M, alpha=0.6, beta=1.0, seed=37):
+        """CovSample (src/Base/string_kernel.py:80-89) without touching the global RNG."""
+        rs = np.random.RandomState(seed)
+        u = rs.rand(max(M - 1, 0))
+        Ms = [1]
+        for i, m in enumerate(range(2, M + 1)):
+            if (1 - (alpha ** (m - Ms[-1] + 1))) * (m ** (-beta)) >= u[i]:
+                Ms.append(m)
+        return Ms
+
+    def _ms(self):
+        lens = [hi - lo for lo, hi in self.window_slices()]
+        return np.asarray(self.cov_sample(max(lens), self.MS_ALPHA, self.MS_BETA, self.MS_SEED), dtype=np.int32)
+
+    def set_window_svcs(self, sv_rows, n_support, dual_coef, intercept, probA, probB):
+        """Install fitted per-window SVCs directly: sv_rows[w] int8 [nSV_w, M_w] (grouped by
+        class), n_support[w] [A], dual_coef[w] [A-1, nSV_w] (SVC._dual_coef_), intercept /
+        probA / probB [w] [A(A-1)/2] (SVC._intercept_, probA_, probB_)."""
+        self.sv_rows = [np.ascontiguousarray(s, dtype=np.int8) for s in sv_rows]
+        self._fitted = dict(n_support=[np.asarray(v, dtype=np.int32) for v in n_support],
+                            dual_coef=[np.ascontiguousarray(v, dtype=np.float64) for v in dual_coef],
+                            intercept=[np.asarray(v, dtype=np.float64) for v in intercept],
+                            probA=[np.asarray(v, dtype=np.float64) for v in probA],
+                            probB=[np.asarray(v, dtype=np.float64) for v in probB])
+        self._handles = {}
+
+    def _make_handle(self, sv_rows, n_support, dual_coef, intercept, probA, probB):
+        P = self.A * (self.A - 1) // 2
+        sv = np.concatenate([s.ravel() for s in sv_rows]) if len(sv_rows) else np.zeros(0, np.int8)
+        ns = np.ascontiguousarray(np.stack(n_support), dtype=np.int32)
+        dc = np.concatenate([d.ravel() for d in dual_coef])
+        ic, pa, pb = (np.ascontiguousarray(np.stack(v).reshape(self.W, P), dtype=np.float64) for v in (intercept, probA, probB))
+        Ms = self._ms()
+        out = C.c_void_p()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib().gnx_svc_model_create(C.byref(out), int(self.A), int(self.C), int(self.M), int(self.context), p(sv), p(ns),
+                                                   p(dc), p(ic), p(pa), p(pb), p(Ms), len(Ms)), "gnx_svc_model_create")
+        return _Handle(out, _lib.lib().gnx_svc_model_destroy)
+
+    def handle(self):
+        import torch
+        key = torch.cuda.current_device()
+        h = self._handles.get(key)
+        if h is None:
+            f = self._fitted
+            h = self._make_handle(self.sv_rows, f["n_support"], f["dual_coef"], f["intercept"], f["probA"], f["probB"])
+            self._handles[key] = h
+        return h.ptr
+
+    def kernel_window(self, w, X, handle=None):
+        """Raw string-kernel values of window w against its support vectors: int32 [N, nSV_w]."""
+        import torch
+        _lib.require_gpu()
+        Xd, ld = to_device_haplotypes(X)
+        nsv = len(self.sv_rows[w]) if handle is None else handle[1]
+        K = torch.empty((Xd.shape[0], nsv), dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().gnx_svc_kernel_window(self.handle() if handle is None else handle[0].ptr, int(w), Xd.data_ptr(),
+                                                    Xd.shape[0], ld, K.data_ptr(), st), "gnx_svc_kernel_window")
+        return K
+
+    def _device_predict(self, Xd, ld, dtype=None):
+        import torch
+        N = Xd.shape[0]
+        Bd = torch.empty((N, self.W, self.A), dtype=torch.float64, device=Xd.device)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().gnx_svc_predict(self.handle(), Xd.data_ptr(), N, ld, Bd.data_ptr(), st), "gnx_svc_predict")
+        return Bd
+
+    def predict_proba(self, X):
+        """[N, W, A] float64 (numpy in -> numpy out, cuda in -> cuda out), as the reference's SVC."""
+        _lib.require_gpu()
+        import torch
+        t = time()
+        Xd, ld = to_device_haplotypes(X)
+        assert Xd.shape[1] == self.C
+        Bd = self._device_predict(Xd, ld)
+        if _is_torch(X) and X.is_cuda:
+            out = Bd
+        else:
+            torch.cuda.current_stream().synchronize()
+            out = Bd.cpu().numpy()
+        self.time["inference"] = time() - t
+        return out
+
+    def train(self, X, y, verbose=True):
+        """Host training (src/Base/base.py:99-127 with SVC windows): Gram matrices from K2,
+        libsvm + Platt scaling through scikit-learn's SVC(kernel="precomputed")."""
+        from sklearn import svm
+        t = time()
+        X = np.asarray(X, dtype=np.int8)
+        n = len(X)
+        Xp = self.pad(X) if self.context != 0 else X
+        # a throw-away model whose "support vectors" are all training rows gives the Gram matrices
+        sl = self.window_slices()
+        rows = [np.ascontiguousarray(Xp[:, lo:hi]) for lo, hi in sl]
+        P = self.A * (self.A - 1) // 2
+        ns0 = np.zeros(self.A, np.int32); ns0[0] = n
+        tmp = self._make_handle(rows, [ns0] * self.W, [np.zeros((self.A - 1, n))] * self.W, [np.zeros(P)] * self.W,
+                                [np.zeros(P)] * self.W, [np.zeros(P)] * self.W)
+        fitted = dict(n_support=[], dual_coef=[], intercept=[], probA=[], probB=[])
+        svs = []
+        for w in range(self.W):
+            G = self.kernel_window(w, X, handle=(tmp, n)).cpu().numpy().astype(np.float64)
+            mdl = svm.SVC(kernel="precomputed", probability=True, random_state=self.seed).fit(G, y[:, w])
+            assert len(mdl.classes_) == self.A, "window %d saw %d classes, need all %d" % (w, len(mdl.classes_), self.A)
+            self.models[w] = mdl
+            svs.append(rows[w][mdl.support_])
+            fitted["n_support"].append(mdl.n_support_)
+            fitted["dual_coef"].append(mdl._dual_coef_)
+            fitted["intercept"].append(mdl._intercept_)
+            fitted["probA"].append(mdl._probA if hasattr(mdl, "_probA") else mdl.probA_)
+            fitted["probB"].append(mdl._probB if hasattr(mdl, "_probB") else mdl.probB_)
+        self.set_window_svcs(svs, fitted["n_support"], fitted["dual_coef"], fitted["intercept"], fitted["probA"], fitted["probB"])
+        self.time["train"] = time() - t

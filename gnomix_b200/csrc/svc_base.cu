@@ -1,0 +1,478 @@
+// svc_base.cu -- K2 + K3: CovRSKBase.predict_proba for all windows.
+//
+// Replaces, per window, sklearn.svm.SVC(kernel=CovRSK_DP_triangular_numbers, probability=
+// True).predict_proba as configured at src/Base/models.py:195-215 and driven by
+// Base.predict_proba_vectorized (src/Base/base.py:146-180):
+//   K2  the string kernel  src/Base/string_kernel.py:91-111
+//         K(x, y) = sum over positions of cov_tri, i.e. (closed form)
+//         K(x, y) = sum_{m in Ms} #{length-m substrings on which x == y everywhere}
+//       evaluated on 2-bit planes of the int8 haplotypes: z = match word (32 SNPs),
+//       R_m = positions ending an all-match stretch of length >= m, K += popc(R_m) for the
+//       short lengths (doubling chain 1,2,4,8,16,32) and a run-length table for the long ones
+//       (a maximal run of length L adds sum_{m in Ms, m > 32, m <= L} (L - m + 1)).
+//   K3  libsvm svm_predict_probability on the precomputed kernel row: pairwise decision
+//       values in support-vector order, Platt sigmoid, pairwise coupling
+//       (multiclass_probability) -- oracle/gnx_oracle.c orc_svc_proba, same operation order.
+//
+// Layout: one launch pair per window.  K2: a CTA owns 64 query haplotypes of the window
+// (bit planes built once in shared memory with warp ballots straight from the int8 matrix,
+// reflect pad applied by index) and streams the window's support vectors through shared
+// memory in chunks; lanes = queries, support vector words are broadcasts.  The kernel row
+// is written transposed (Kt[sv][hap]) so that K2's stores and K3's loads are coalesced.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gnx {
+
+constexpr int SVC_MAX_A = 16;
+constexpr int SVC_Q = 64;        // query haplotypes per CTA
+constexpr int SVC_CHUNK = 64;    // support vectors staged per pass
+constexpr int SVC_THREADS = 256;
+
+struct SvcWin {
+    int64_t lo;       // first padded column of the window
+    int len, nw, nwp; // features, 32-bit words, padded (odd) word stride
+    int nsv;
+    const uint32_t* planes;   // [nsv][2][nw]
+    const double* coef;       // [A-1][nsv]
+    const int32_t* n_support; // [A]
+    const double *intercept, *probA, *probB;  // [P]
+};
+
+struct SvcDev {
+    int A, P, W, fast, small_mask, min_big;
+    int64_t C, M, ctx;
+    const int32_t* gbig;   // [maxlen+1] run-length table of the lengths > 32
+    const uint8_t* ohe;    // [maxlen+2] 1 iff length in Ms (generic path)
+};
+
+__device__ __forceinline__ int64_t svc_pad_to_orig(int64_t p, int64_t C, int64_t ctx) {
+    if (p < ctx) return ctx - 1 - p;
+    if (p >= ctx + C) return 2 * C + ctx - 1 - p;
+    return p - ctx;
+}
+
+// ------------------------------------------------------------------------------ K2
+// grid.x = ceil(N / 64).  Kt != NULL: Kt[s * ldK + n]; else Krow[n * nsv + s].
+__global__ void __launch_bounds__(SVC_THREADS, 2)
+svc_kernel_window(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, int64_t ldX, int32_t* __restrict__ Kt, int64_t ldK,
+                  int32_t* __restrict__ Krow) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    uint32_t* qp = sm;                               // [64][2][nwp]
+    uint32_t* sp = sm + (size_t)SVC_Q * 2 * w.nwp;   // [SVC_CHUNK][2][nw]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n0 = (int64_t)blockIdx.x * SVC_Q;
+    const int nw = w.nw, nwp = w.nwp;
+
+    // ---- query bit planes: one warp per haplotype, 32 SNPs per ballot
+    for (int q = warp; q < SVC_Q; q += SVC_THREADS / 32) {
+        const int64_t n = n0 + q;
+        for (int j = 0; j < nw; j++) {
+            const int p = j * 32 + lane;
+            int v = 0;
+            if (n < N && p < w.len) v = X[n * ldX + svc_pad_to_orig(w.lo + p, m.C, m.ctx)];
+            const uint32_t b0 = __ballot_sync(0xffffffffu, v & 1), b1 = __ballot_sync(0xffffffffu, v & 2);
+            if (lane == 0) {
+                qp[(q * 2 + 0) * nwp + j] = b0;
+                qp[(q * 2 + 1) * nwp + j] = b1;
+            }
+        }
+    }
+    const uint32_t tail = (w.len & 31) ? ((1u << (w.len & 31)) - 1u) : 0xffffffffu;
+    const uint32_t* q0a = qp + ((lane) * 2) * nwp;
+    const uint32_t* q1a = qp + ((lane + 32) * 2) * nwp;
+
+    for (int s0 = 0; s0 < w.nsv; s0 += SVC_CHUNK) {
+        const int ns = min(SVC_CHUNK, w.nsv - s0);
+        __syncthreads();
+        {
+            const uint32_t* src = w.planes + (size_t)s0 * 2 * nw;
+            for (int i = threadIdx.x; i < ns * 2 * nw; i += SVC_THREADS) sp[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        // warp handles support vectors warp*8 .. warp*8+7 of the chunk, 4 at a time, x 2 queries per lane
+        for (int sb = warp * 8; sb < warp * 8 + 8 && sb < ns; sb += 4) {
+            int K[2][4];
+            uint32_t zp[2][4], r2p[2][4], r4p[2][4], r8p[2][4], r16p[2][4];
+            int run[2][4];
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    K[a][b] = 0;
+                    zp[a][b] = r2p[a][b] = r4p[a][b] = r8p[a][b] = r16p[a][b] = 0u;
+                    run[a][b] = 0;
+                }
+            for (int j = 0; j < nw; j++) {
+                uint32_t xq[2][2];
+                xq[0][0] = q0a[j]; xq[0][1] = q0a[nwp + j];
+                xq[1][0] = q1a[j]; xq[1][1] = q1a[nwp + j];
+                const uint32_t msk = (j == nw - 1) ? tail : 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int s = min(sb + b, ns - 1);
+                    const uint32_t y0 = sp[(s * 2 + 0) * nw + j], y1 = sp[(s * 2 + 1) * nw + j];
+#pragma unroll
+                    for (int a = 0; a < 2; a++) {
+                        const uint32_t z = ~((xq[a][0] ^ y0) | (xq[a][1] ^ y1)) & msk;
+                        int k = 0;
+                        if (m.small_mask & 1) k += __popc(z);
+                        const uint32_t r2 = z & __funnelshift_l(zp[a][b], z, 1);
+                        if (m.small_mask & 2) k += __popc(r2);
+                        const uint32_t r4 = r2 & __funnelshift_l(r2p[a][b], r2, 2);
+                        if (m.small_mask & 4) k += __popc(r4);
+                        const uint32_t r8 = r4 & __funnelshift_l(r4p[a][b], r4, 4);
+                        if (m.small_mask & 8) k += __popc(r8);
+                        if (m.small_mask & 48) {
+                            const uint32_t r16 = r8 & __funnelshift_l(r8p[a][b], r8, 8);
+                            if (m.small_mask & 16) k += __popc(r16);
+                            if (m.small_mask & 32) k += __popc(r16 & __funnelshift_l(r16p[a][b], r16, 16));
+                            r16p[a][b] = r16;
+                        }
+                        zp[a][b] = z; r2p[a][b] = r2; r4p[a][b] = r4; r8p[a][b] = r8;
+                        // maximal runs longer than 32 (they cross a word boundary)
+                        if (z == 0xffffffffu) {
+                            run[a][b] += 32;
+                        } else {
+                            const int L = run[a][b] + (__ffs(~z) - 1);
+                            if (L >= m.min_big) k += __ldg(m.gbig + L);
+                            run[a][b] = __clz(~z);
+                        }
+                        K[a][b] += k;
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    int k = K[a][b];
+                    if (run[a][b] >= m.min_big) k += __ldg(m.gbig + run[a][b]);
+                    const int64_t n = n0 + lane + 32 * a;
+                    const int s = s0 + sb + b;
+                    if (n < N && sb + b < ns) {
+                        if (Kt) Kt[(int64_t)s * ldK + n] = k;
+                        else Krow[n * w.nsv + s] = k;
+                    }
+                }
+        }
+    }
+}
+
+// Generic path (any Ms): the reference's DP verbatim per (query, support vector) pair --
+// tri = current match-run length, cov += [tri in Ms], K += cov (string_kernel.py:94-100).
+__global__ void svc_kernel_window_generic(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, int64_t ldX,
+                                          int32_t* __restrict__ Kt, int64_t ldK, int32_t* __restrict__ Krow) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (n >= N) return;
+    const uint32_t* y0 = w.planes + (size_t)s * 2 * w.nw;
+    const uint32_t* y1 = y0 + w.nw;
+    int tri = 0, cov = 0, k = 0;
+    for (int p = 0; p < w.len; p++) {
+        const int x = X[n * ldX + svc_pad_to_orig(w.lo + p, m.C, m.ctx)] & 3;
+        const int y = ((y0[p >> 5] >> (p & 31)) & 1) | (((y1[p >> 5] >> (p & 31)) & 1) << 1);
+        if (x == y) {
+            tri++;
+            cov += m.ohe[tri];
+            k += cov;
+        } else {
+            tri = 0;
+            cov = 0;
+        }
+    }
+    if (Kt) Kt[(int64_t)s * ldK + n] = k;
+    else Krow[n * w.nsv + s] = k;
+}
+
+// ------------------------------------------------------------------------------ K3
+__device__ void svc_multiclass_probability(int k, const double* r, double* p) {
+    int t, j, iter = 0, max_iter = k > 100 ? k : 100;
+    double Q[SVC_MAX_A * SVC_MAX_A], Qp[SVC_MAX_A], pQp, eps = 0.005 / k;
+    for (t = 0; t < k; t++) {
+        p[t] = 1.0 / k;
+        Q[t * k + t] = 0;
+        for (j = 0; j < t; j++) {
+            Q[t * k + t] += r[j * k + t] * r[j * k + t];
+            Q[t * k + j] = Q[j * k + t];
+        }
+        for (j = t + 1; j < k; j++) {
+            Q[t * k + t] += r[j * k + t] * r[j * k + t];
+            Q[t * k + j] = -r[j * k + t] * r[t * k + j];
+        }
+    }
+    for (iter = 0; iter < max_iter; iter++) {
+        pQp = 0;
+        for (t = 0; t < k; t++) {
+            Qp[t] = 0;
+            for (j = 0; j < k; j++) Qp[t] += Q[t * k + j] * p[j];
+            pQp += p[t] * Qp[t];
+        }
+        double max_error = 0;
+        for (t = 0; t < k; t++) {
+            double error = fabs(Qp[t] - pQp);
+            if (error > max_error) max_error = error;
+        }
+        if (max_error < eps) break;
+        for (t = 0; t < k; t++) {
+            double diff = (-Qp[t] + pQp) / Q[t * k + t];
+            p[t] += diff;
+            pQp = (pQp + diff * (diff * Q[t * k + t] + 2 * Qp[t])) / (1 + diff) / (1 + diff);
+            for (j = 0; j < k; j++) {
+                Qp[j] = (Qp[j] + diff * Q[t * k + j]) / (1 + diff);
+                p[j] /= (1 + diff);
+            }
+        }
+    }
+}
+
+// thread = one haplotype; one pass over the support vectors in order feeds all pairwise sums
+__global__ void __launch_bounds__(128)
+svc_proba_window(SvcDev m, SvcWin w, int wi, const int32_t* __restrict__ Kt, int64_t ldK, int64_t N, double* __restrict__ B) {
+    __shared__ int s_start[SVC_MAX_A + 1];
+    if (threadIdx.x == 0) {
+        s_start[0] = 0;
+        for (int c = 0; c < m.A; c++) s_start[c + 1] = s_start[c] + w.n_support[c];
+    }
+    __syncthreads();
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int k = m.A;
+    double sum[SVC_MAX_A * (SVC_MAX_A - 1) / 2];
+    for (int p = 0; p < m.P; p++) sum[p] = 0.0;
+    // pair index of (i, j), i < j, in libsvm order
+    auto pidx = [k](int i, int j) { return i * k - i * (i + 1) / 2 + (j - i - 1); };
+    for (int c = 0; c < k; c++) {
+        for (int s = s_start[c]; s < s_start[c + 1]; s++) {
+            const double kv = (double)Kt[(int64_t)s * ldK + n];
+            for (int d = 0; d < k; d++) {
+                if (d == c) continue;
+                // class c plays "i" against d > c (coef row d-1) and "j" against d < c (coef row d)
+                const double cf = (d > c) ? __ldg(w.coef + (size_t)(d - 1) * w.nsv + s) : __ldg(w.coef + (size_t)d * w.nsv + s);
+                const int p = (d > c) ? pidx(c, d) : pidx(d, c);
+                sum[p] += cf * kv;
+            }
+        }
+    }
+    double pair[SVC_MAX_A * SVC_MAX_A];
+    int p = 0;
+    for (int i = 0; i < k; i++)
+        for (int j = i + 1; j < k; j++) {
+            const double dec = sum[p] + w.intercept[p];
+            const double fApB = dec * w.probA[p] + w.probB[p];
+            double v;
+            if (fApB >= 0)
+                v = gnx_exp(-fApB) / (1.0 + gnx_exp(-fApB));
+            else
+                v = 1.0 / (1 + gnx_exp(fApB));
+            if (v < 1e-7) v = 1e-7;
+            if (v > 1 - 1e-7) v = 1 - 1e-7;
+            pair[i * k + j] = v;
+            pair[j * k + i] = 1 - v;
+            p++;
+        }
+    double* out = B + (n * m.W + wi) * k;
+    if (k == 2) {
+        out[0] = pair[1];
+        out[1] = pair[2];
+    } else {
+        double pr[SVC_MAX_A];
+        svc_multiclass_probability(k, pair, pr);
+        for (int c = 0; c < k; c++) out[c] = pr[c];
+    }
+}
+
+}  // namespace gnx
+
+struct gnx_svc {
+    gnx::SvcDev d;
+    std::vector<gnx::SvcWin> win;
+    int device;
+    int max_nsv;
+    void* d_blob;
+};
+
+using namespace gnx;
+
+extern "C" {
+
+int gnx_svc_model_create(gnx_svc_t** out, int A, int64_t C, int64_t M, int64_t ctx, const int8_t* sv, const int32_t* n_support,
+                         const double* dual_coef, const double* intercept, const double* probA, const double* probB,
+                         const int32_t* Ms, int n_ms) {
+    GNX_REQUIRE(out != nullptr, "gnx_svc_model_create: out is NULL");
+    *out = nullptr;
+    GNX_REQUIRE(A >= 2 && A <= SVC_MAX_A, "gnx_svc_model_create: A=%d unsupported (2..%d)", A, SVC_MAX_A);
+    GNX_REQUIRE(C > 0 && M > 0 && M <= C && ctx >= 0 && ctx <= C, "gnx_svc_model_create: bad geometry");
+    GNX_REQUIRE(sv && n_support && dual_coef && intercept && probA && probB && Ms && n_ms > 0, "gnx_svc_model_create: NULL array");
+    if (require_blackwell()) return 1;
+    const int64_t W = C / M, rem = C - M * W, M_ = M + 2 * ctx;
+    const int P = A * (A - 1) / 2;
+    const int64_t maxlen = M_ + rem;
+    // run-length tables
+    std::vector<uint8_t> ohe(maxlen + 2, 0);
+    int small_mask = 0, min_big = 0x7fffffff;
+    bool fast = true;
+    for (int i = 0; i < n_ms; i++) {
+        const int mm = Ms[i];
+        GNX_REQUIRE(mm >= 1, "gnx_svc_model_create: Ms[%d]=%d", i, mm);
+        if (mm <= maxlen) ohe[mm] = 1;
+        if (mm <= 32) {
+            if ((mm & (mm - 1)) == 0) small_mask |= mm;
+            else fast = false;
+        } else {
+            min_big = std::min(min_big, mm);
+        }
+    }
+    std::vector<int32_t> gbig(maxlen + 1, 0);
+    for (int64_t L = 1; L <= maxlen; L++) {
+        int64_t g = 0;
+        for (int i = 0; i < n_ms; i++)
+            if (Ms[i] > 32 && Ms[i] <= L) g += L - Ms[i] + 1;
+        gbig[L] = (int32_t)g;
+    }
+    // per-window packing
+    gnx_svc* m = new gnx_svc();
+    m->win.resize(W);
+    std::vector<uint32_t> planes;
+    std::vector<double> coef;
+    std::vector<size_t> plane_off(W), coef_off(W);
+    int64_t sv_off = 0, coef_in = 0;
+    int max_nsv = 0;
+    for (int64_t w = 0; w < W; w++) {
+        int nsv = 0;
+        for (int c = 0; c < A; c++) {
+            GNX_REQUIRE(n_support[w * A + c] >= 0, "gnx_svc_model_create: negative n_support");
+            nsv += n_support[w * A + c];
+        }
+        const int len = (int)((w == W - 1) ? (M_ + rem) : M_);
+        const int nw = (len + 31) / 32;
+        SvcWin& sw = m->win[w];
+        sw.lo = (w == W - 1) ? (C + 2 * ctx - (M_ + rem)) : w * M;
+        sw.len = len; sw.nw = nw; sw.nwp = nw | 1; sw.nsv = nsv;
+        plane_off[w] = planes.size();
+        planes.resize(planes.size() + (size_t)nsv * 2 * nw, 0u);
+        uint32_t* pw = planes.data() + plane_off[w];
+        for (int s = 0; s < nsv; s++) {
+            const int8_t* row = sv + sv_off + (int64_t)s * len;
+            for (int p = 0; p < len; p++) {
+                const int v = row[p];
+                if (v < 0 || v > 3) {
+                    delete m;
+                    set_error("gnx_svc_model_create: support vector value %d outside 0..3 (window %lld)", v, (long long)w);
+                    return 2;
+                }
+                if (v & 1) pw[((size_t)s * 2 + 0) * nw + (p >> 5)] |= 1u << (p & 31);
+                if (v & 2) pw[((size_t)s * 2 + 1) * nw + (p >> 5)] |= 1u << (p & 31);
+            }
+        }
+        sv_off += (int64_t)nsv * len;
+        coef_off[w] = coef.size();
+        coef.insert(coef.end(), dual_coef + coef_in, dual_coef + coef_in + (int64_t)(A - 1) * nsv);
+        coef_in += (int64_t)(A - 1) * nsv;
+        max_nsv = std::max(max_nsv, nsv);
+    }
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_pl = 0, o_cf = al(planes.size() * 4), o_ns = o_cf + al(coef.size() * 8), o_ic = o_ns + al((size_t)W * A * 4),
+                 o_pa = o_ic + al((size_t)W * P * 8), o_pb = o_pa + al((size_t)W * P * 8), o_gb = o_pb + al((size_t)W * P * 8),
+                 o_oh = o_gb + al(gbig.size() * 4), total = o_oh + al(ohe.size());
+    char* blob = nullptr;
+    cudaError_t e = cudaMalloc((void**)&blob, total);
+    if (e != cudaSuccess) {
+        delete m;
+        set_error("gnx_svc_model_create: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+        return 1;
+    }
+    bool ok = true;
+    ok &= cudaMemcpy(blob + o_pl, planes.data(), planes.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + o_cf, coef.data(), coef.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + o_ns, n_support, (size_t)W * A * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + o_ic, intercept, (size_t)W * P * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + o_pa, probA, (size_t)W * P * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + o_pb, probB, (size_t)W * P * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + o_gb, gbig.data(), gbig.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + o_oh, ohe.data(), ohe.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        cudaFree(blob);
+        delete m;
+        set_error("gnx_svc_model_create: H2D copy failed");
+        return 1;
+    }
+    for (int64_t w = 0; w < W; w++) {
+        SvcWin& sw = m->win[w];
+        sw.planes = reinterpret_cast<const uint32_t*>(blob + o_pl) + plane_off[w];
+        sw.coef = reinterpret_cast<const double*>(blob + o_cf) + coef_off[w];
+        sw.n_support = reinterpret_cast<const int32_t*>(blob + o_ns) + w * A;
+        sw.intercept = reinterpret_cast<const double*>(blob + o_ic) + w * P;
+        sw.probA = reinterpret_cast<const double*>(blob + o_pa) + w * P;
+        sw.probB = reinterpret_cast<const double*>(blob + o_pb) + w * P;
+    }
+    cudaGetDevice(&m->device);
+    m->d_blob = blob;
+    m->max_nsv = max_nsv;
+    m->d = SvcDev{A, P, (int)W, fast ? 1 : 0, small_mask, min_big, C, M, ctx, reinterpret_cast<const int32_t*>(blob + o_gb),
+                  reinterpret_cast<const uint8_t*>(blob + o_oh)};
+    *out = m;
+    return 0;
+}
+
+void gnx_svc_model_destroy(gnx_svc_t* m) {
+    if (!m) return;
+    if (m->d_blob) cudaFree(m->d_blob);
+    delete m;
+}
+
+static int svc_launch_kernel(const gnx_svc_t* m, int w, const int8_t* X, int64_t N, int64_t ldX, int32_t* Kt, int64_t ldK, int32_t* Krow,
+                             cudaStream_t st) {
+    const SvcWin& sw = m->win[w];
+    if (sw.nsv == 0) return 0;
+    if (m->d.fast) {
+        const size_t smem = ((size_t)SVC_Q * 2 * sw.nwp + (size_t)SVC_CHUNK * 2 * sw.nw) * 4;
+        GNX_REQUIRE(smem <= 227 * 1024, "gnx_svc: window of %d SNPs too long for shared memory", sw.len);
+        GNX_CUDA(cudaFuncSetAttribute(svc_kernel_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        svc_kernel_window<<<(unsigned)ceil_div(N, SVC_Q), SVC_THREADS, smem, st>>>(m->d, sw, X, N, ldX, Kt, ldK, Krow);
+    } else {
+        dim3 grid((unsigned)ceil_div(N, 128), (unsigned)sw.nsv);
+        svc_kernel_window_generic<<<grid, 128, 0, st>>>(m->d, sw, X, N, ldX, Kt, ldK, Krow);
+    }
+    GNX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gnx_svc_kernel_window(const gnx_svc_t* m, int w, const int8_t* X_dev, int64_t N, int64_t ldX, int32_t* K_dev, void* stream) {
+    GNX_REQUIRE(m != nullptr, "gnx_svc_kernel_window: NULL model");
+    GNX_REQUIRE(w >= 0 && w < m->d.W, "gnx_svc_kernel_window: window %d outside 0..%d", w, m->d.W - 1);
+    GNX_REQUIRE(N >= 0 && ldX >= m->d.C, "gnx_svc_kernel_window: bad shape");
+    if (N == 0) return 0;
+    GNX_REQUIRE(X_dev && K_dev, "gnx_svc_kernel_window: NULL buffer");
+    return svc_launch_kernel(m, w, X_dev, N, ldX, nullptr, 0, K_dev, (cudaStream_t)stream);
+}
+
+int gnx_svc_predict(const gnx_svc_t* m, const int8_t* X_dev, int64_t N, int64_t ldX, double* B_dev, void* stream) {
+    GNX_REQUIRE(m != nullptr, "gnx_svc_predict: NULL model");
+    GNX_REQUIRE(N >= 0 && ldX >= m->d.C, "gnx_svc_predict: bad shape N=%lld ldX=%lld", (long long)N, (long long)ldX);
+    if (N == 0) return 0;
+    GNX_REQUIRE(X_dev && B_dev, "gnx_svc_predict: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ldK = (N + 31) & ~int64_t(31);
+    int32_t* Kt = nullptr;
+    GNX_CUDA(cudaMallocAsync((void**)&Kt, sizeof(int32_t) * (size_t)std::max(1, m->max_nsv) * ldK, st));
+    int rc = 0;
+    for (int w = 0; w < m->d.W && rc == 0; w++) {
+        rc = svc_launch_kernel(m, w, X_dev, N, ldX, Kt, ldK, nullptr, st);
+        if (rc) break;
+        svc_proba_window<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(m->d, m->win[w], w, Kt, ldK, N, B_dev);
+        if (cudaGetLastError() != cudaSuccess) {
+            set_error("gnx_svc_predict: launch failed (window %d)", w);
+            rc = 1;
+        }
+    }
+    cudaFreeAsync(Kt, st);
+    return rc;
+}
+
+}  // extern "C"
