@@ -21,6 +21,7 @@ _SIGS = {
     "gnx_version": (C.c_int, []),
     "gnx_last_error": (C.c_char_p, []),
     "gnx_device_count": (C.c_int, []),
+    "gnx_selftest_math": (C.c_int, [c_i64, C.c_uint64, c_vp]),
     "gnx_lr_model_create": (C.c_int, [C.POINTER(c_vp), C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, C.c_int]),
     "gnx_lr_model_destroy": (None, [c_vp]),
     "gnx_lr_model_scale": (C.c_int, [c_vp]),

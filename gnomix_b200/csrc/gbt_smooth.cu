@@ -59,9 +59,9 @@ gbt_smooth_kernel(GbtDev m, size_t forest_bytes, const float* __restrict__ B, in
 // is: node word -> (byte offset of the feature in the row, threshold index) -> one
 // integer compare against the pre-ranked input.  Rank rows hold rank << 16, node words
 // are (k << 16 | byte offset), so `x < thr`  <=>  !(rank_word > node_word).
-template <int AT>
+template <int AT, bool TOPC>
 __global__ void __launch_bounds__(RK_THREADS, 1)
-gbt_smooth_rank_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes,
+gbt_smooth_rank_kernel(const __grid_constant__ GbtTopC topc, GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes,
                        const float* __restrict__ B, int64_t N, int W, int G,
                        float* __restrict__ proba, int32_t* __restrict__ label) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -122,7 +122,8 @@ gbt_smooth_rank_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, s
             const int64_t n = g0 + h;
             const unsigned char* row = reinterpret_cast<const unsigned char*>(rk + h * hap_words + w * ast);
             float psum[AMAX];
-            gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
+            if (TOPC) gbt_rank_walk_c<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
+            else gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
             gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
         }
     }
@@ -276,6 +277,13 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->rank_forest_bytes = rb;
     m->rank_forest = reinterpret_cast<const unsigned char*>(blob + forest + 256);
     m->use_rank = 1;
+    m->h_topc = nullptr;
+    if (rank_ok && n_trees <= GBT_TOPC_MAX_T) {
+        m->h_topc = new GbtTopC();
+        const uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
+        for (int t = 0; t < n_trees; t++)
+            for (int k = 0; k < 3; k++) m->h_topc->w[3 * t + k] = top[(size_t)t * 4 + k];
+    }
     *out = m;
     return 0;
 }
@@ -283,6 +291,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
 void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     if (!m) return;
     if (m->d_blob) cudaFree(m->d_blob);
+    delete m->h_topc;
     delete m;
 }
 
@@ -326,9 +335,16 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
             const int grid = (int)std::min<int64_t>(ceil_div(N, bestG), (int64_t)sm_count());
 #define CALLR(AT)                                                                                                              \
     do {                                                                                                                       \
-        GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        gbt_smooth_rank_kernel<AT><<<grid, RK_THREADS, smem, st>>>(m->d, m->rank_forest, m->rank_forest_bytes, B_dev, N, W,  \
-                                                                   bestG, proba_dev, label_dev);                              \
+        if (m->h_topc) {                                                                                                       \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_rank_kernel<AT, true><<<grid, RK_THREADS, smem, st>>>(*m->h_topc, m->d, m->rank_forest, m->rank_forest_bytes, \
+                                                                             B_dev, N, W, bestG, proba_dev, label_dev);        \
+        } else {                                                                                                               \
+            static const GbtTopC none{};                                                                                       \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_rank_kernel<AT, false><<<grid, RK_THREADS, smem, st>>>(none, m->d, m->rank_forest, m->rank_forest_bytes, \
+                                                                              B_dev, N, W, bestG, proba_dev, label_dev);       \
+        }                                                                                                                      \
     } while (0)
             GBT_DISPATCH_A(m->d.A, CALLR)
 #undef CALLR

@@ -60,9 +60,9 @@ __device__ __forceinline__ void gbt_finish(const GbtDev& m, float* psum, float* 
     for (int c = 0; c < AMAX; c++)
         if (c < A) {
             psum[c] = gnx_expf_cr(GNX_FSUB(psum[c], wmax));
-            wsum = GNX_ADD(wsum, (double)psum[c]);
+            wsum = GNX_ADD(wsum, GNX_F2D(psum[c]));
         }
-    const float ws = (float)wsum;
+    const float ws = GNX_D2F(wsum);
     int best = 0;
     float pbest = 0.f;
 #pragma unroll
@@ -154,6 +154,48 @@ __device__ __forceinline__ void gbt_rank_walk(int A, const unsigned char* __rest
     }
 }
 
+// Same walk with the top three nodes of every tree read from the kernel parameter bank
+// (warp-uniform index -> constant-cache broadcast instead of a shared-memory wavefront).
+constexpr int GBT_TOPC_MAX_T = 2048;
+struct GbtTopC {
+    uint32_t w[3 * GBT_TOPC_MAX_T];
+};
+
+template <int AT>
+__device__ __forceinline__ void gbt_rank_walk_c(int A, const unsigned char* __restrict__ row, const GbtTopC& top,
+                                                const uint32_t* __restrict__ lw, const float* __restrict__ lv, int rounds,
+                                                float* psum) {
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+    int tbase = 0;
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const uint32_t t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
+                const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (t0 & 0xffffu));
+                const bool b0 = x0 > t0;
+                const uint32_t n1 = b0 ? t2 : t1;
+                const uint32_t x1 = *reinterpret_cast<const uint32_t*>(row + (n1 & 0xffffu));
+                const bool b1 = x1 > n1;
+                const int i2 = (b0 ? 2 : 0) + (b1 ? 1 : 0);
+                const uint32_t n2 = lw[c * RK_LOWER + i2];
+                const uint32_t x2 = *reinterpret_cast<const uint32_t*>(row + (n2 & 0xffffu));
+                const int i3 = 2 * i2 + ((x2 > n2) ? 1 : 0);
+                const uint32_t n3 = lw[c * RK_LOWER + 4 + i3];
+                const uint32_t x3 = *reinterpret_cast<const uint32_t*>(row + (n3 & 0xffffu));
+                const int lf = 2 * i3 + ((x3 > n3) ? 1 : 0);
+                psum[c] = GNX_FADD(psum[c], lv[c * RK_LEAVES + lf]);
+            }
+        }
+        tbase += 3 * A;
+        lw += RK_LOWER * A;
+        lv += RK_LEAVES * A;
+    }
+}
+
 // One tree of the rank-form forest for one row: returns the leaf value.
 __device__ __forceinline__ float gbt_rank_tree(const unsigned char* __restrict__ row, const uint4 t4,
                                                const uint32_t* __restrict__ lw, const float* __restrict__ lv) {
@@ -181,4 +223,5 @@ struct gnx_gbt {
     size_t rank_forest_bytes;  // lower | leaves | top, contiguous (shared-memory image of the fast path)
     const unsigned char* rank_forest;
     int use_rank;            // 1 = rank-form kernel when eligible (default), 0 = generic float traversal
+    gnx::GbtTopC* h_topc;    // host copy of the top nodes for the parameter-bank variant (NULL if T too large)
 };

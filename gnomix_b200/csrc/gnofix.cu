@@ -189,8 +189,8 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
                 team_sync(team);
                 if (tid < 4) {
                     double wsum = 0.0;
-                    for (int k = 0; k < A; k++) wsum = GNX_ADD(wsum, (double)expv[tid * GBT_MAX_A + k]);
-                    const float ws = (float)wsum;
+                    for (int k = 0; k < A; k++) wsum = GNX_ADD(wsum, GNX_F2D(expv[tid * GBT_MAX_A + k]));
+                    const float ws = GNX_D2F(wsum);
                     float best = 0.f;
                     for (int k = 0; k < A; k++) {
                         const float p = GNX_FDIV(expv[tid * GBT_MAX_A + k], ws);

@@ -124,6 +124,7 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
     GNX_REQUIRE(L >= 2, "gnx_lr_model_create: limbs=%d too small", L);
     const int64_t W = C / M, rem = C - M * W, M_ = M + 2 * ctx;
     GNX_REQUIRE(W < (1 << 30), "too many windows");
+    GNX_REQUIRE(M_ + rem <= 32000, "gnx_lr_model_create: windows of %lld SNPs exceed the 32000 the int32 limb accumulators allow", (long long)(M_ + rem));
 
     // padded window ranges, folded original ranges
     std::vector<int64_t> lo(W), len(W), s0(W), e0(W), coff(W);
@@ -194,6 +195,14 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
             m->h_chunk_wn[k]++;
         }
 
+    m->h_chunk_sched.assign((size_t)n_chunks * 4, 0u);
+    for (int k = 0; k < n_chunks; k++)
+        for (int i = 0; i < std::min(4, m->h_chunk_wn[k]); i++) {
+            const int w = m->h_chunk_w0[k] + i;
+            const uint32_t tile = (uint32_t)(m->h_tile_off[w] + (k - m->h_k0[w]));
+            m->h_chunk_sched[(size_t)k * 4 + i] = (tile << 3) | 4u | ((k == m->h_kend[w] - 1) ? 2u : 0u) | ((k == m->h_k0[w]) ? 1u : 0u);
+        }
+
     // pass 2: quantise, fold (int64), split into limbs, scatter into tiles
     std::vector<int8_t> tiles((size_t)n_tiles * LR_TILE_BYTES, 0);
     {
@@ -228,7 +237,8 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_tiles = 0, o_bias = al(tiles.size()), o_k0 = o_bias + al(sizeof(double) * W * Ar),
                  o_kend = o_k0 + al(4 * W), o_toff = o_kend + al(4 * W), o_cw0 = o_toff + al(4 * W),
-                 o_cwn = o_cw0 + al(4 * (size_t)n_chunks), total = o_cwn + al(4 * (size_t)n_chunks);
+                 o_cwn = o_cw0 + al(4 * (size_t)n_chunks), o_sch = o_cwn + al(4 * (size_t)n_chunks),
+                 total = o_sch + al(16 * (size_t)n_chunks);
     char* blob = nullptr;
     cudaError_t e = cudaMalloc((void**)&blob, total);
     if (e != cudaSuccess) {
@@ -245,6 +255,7 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
     ok &= cudaMemcpy(blob + o_toff, m->h_tile_off.data(), 4 * W, cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(blob + o_cw0, m->h_chunk_w0.data(), 4 * (size_t)n_chunks, cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(blob + o_cwn, m->h_chunk_wn.data(), 4 * (size_t)n_chunks, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(blob + o_sch, m->h_chunk_sched.data(), 16 * (size_t)n_chunks, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         cudaFree(blob);
         delete m;
@@ -253,7 +264,7 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
     }
     LrDev& d = m->d;
     d.A = A; d.Ar = Ar; d.L = L; d.apad = apad; d.s = s; d.W = (int)W;
-    d.C = C; d.M = M; d.ctx = ctx; d.n_chunks = n_chunks;
+    d.C = C; d.M = M; d.ctx = ctx; d.n_chunks = n_chunks; d.dbg = 0;
     d.wt = reinterpret_cast<const int8_t*>(blob + o_tiles);
     d.bias = reinterpret_cast<const double*>(blob + o_bias);
     d.k0 = reinterpret_cast<const int32_t*>(blob + o_k0);
@@ -261,6 +272,7 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
     d.tile_off = reinterpret_cast<const int32_t*>(blob + o_toff);
     d.chunk_w0 = reinterpret_cast<const int32_t*>(blob + o_cw0);
     d.chunk_wn = reinterpret_cast<const int32_t*>(blob + o_cwn);
+    d.chunk_sched = reinterpret_cast<const uint4*>(blob + o_sch);
     *out = m;
     return 0;
 }

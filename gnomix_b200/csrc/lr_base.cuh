@@ -16,6 +16,7 @@ struct LrDev {
     int A, Ar, L, apad, s, W;
     int64_t C, M, ctx;
     int n_chunks;
+    int dbg;                   // profiling switches (GNX_LR_DBG): 1 = no MMA, 2 = no MMA + no epilogue math, 4 = no weight loads
     const int8_t* wt;          // [n_tiles][LR_NCOLS][LR_KC] int8 limb planes; column = limb*apad + class
     const double* bias;        // [W][Ar]
     const int32_t* k0;         // [W] first chunk of window w
@@ -23,6 +24,7 @@ struct LrDev {
     const int32_t* tile_off;   // [W] tile index of (w, k0[w])
     const int32_t* chunk_w0;   // [n_chunks] first window covering chunk k
     const int32_t* chunk_wn;   // [n_chunks] number of windows covering chunk k
+    const uint4* chunk_sched;  // [n_chunks] i-th covering window: tile << 3 | valid << 2 | last chunk << 1 | first chunk
 };
 
 }  // namespace gnx
@@ -33,6 +35,7 @@ struct gnx_lr {
     int kernel_sel;  // 0 tcgen05, 1 dp4a
     int n_tiles;
     std::vector<int32_t> h_k0, h_kend, h_tile_off, h_chunk_w0, h_chunk_wn;
+    std::vector<uint32_t> h_chunk_sched;
     void* d_blob;    // single allocation holding every table
     // TMA descriptor of the weight tensor (128 bytes, CUtensorMap) -- built lazily
     alignas(64) unsigned char tmap_w[128];
@@ -43,6 +46,13 @@ namespace gnx {
 
 int lr_launch_tc(const gnx_lr* m, const int8_t* X, int64_t N, int64_t ldX, void* B, bool f64, cudaStream_t st);
 int lr_launch_dp4a_any(const gnx_lr* m, const int8_t* X, int64_t N, int64_t ldX, void* B, bool f64, cudaStream_t st);
+
+template <typename OutT>
+__device__ __forceinline__ OutT lr_out(double v);
+template <>
+__device__ __forceinline__ double lr_out<double>(double v) { return v; }
+template <>
+__device__ __forceinline__ float lr_out<float>(double v) { return GNX_D2F(v); }
 
 // (hap, window) epilogue shared by both kernels: limb recombination (exact int64),
 // scale, intercept, expit, row-normalise (sklearn _predict_proba_lr), store.
@@ -55,17 +65,23 @@ __device__ __forceinline__ void lr_epilogue_store(const int32_t (&acc)[LR_NCOLS]
     const double scale = gnx_pow2i(-m.s);
 #pragma unroll
     for (int a = 0; a < APAD; a++) {
+        // limbs pairwise in int32 first (|acc| < 2^23 for windows <= 32768 SNPs, checked at model
+        // create), then three exact 64-bit steps: tot = sum_l acc_l * 256^l
         long long tot = 0;
 #pragma unroll
-        for (int l = LMAX - 1; l >= 0; l--)
-            if (l < m.L) tot = tot * 256 + (long long)acc[l * APAD + a];
+        for (int j = LMAX / 2 - 1 + (LMAX & 1); j >= 0; j--) {
+            int pr = 0;
+            if (2 * j + 1 < LMAX && 2 * j + 1 < m.L) pr = acc[(2 * j + 1) * APAD + a] * 256;
+            if (2 * j < m.L) pr += acc[(2 * j) * APAD + a];
+            tot = tot * 65536 + (long long)pr;
+        }
         d[a] = 0.0;
-        if (a < m.Ar) d[a] = GNX_ADD(GNX_MUL(__ll2double_rn(tot), scale), __ldg(m.bias + (int64_t)w * m.Ar + a));
+        if (a < m.Ar) d[a] = GNX_ADD(GNX_MUL(GNX_LL2D(tot), scale), __ldg(m.bias + (int64_t)w * m.Ar + a));
     }
     if (m.A == 2) {
         double p = gnx_expit(d[0]);
-        out[0] = (OutT)GNX_SUB(1.0, p);
-        out[1] = (OutT)p;
+        out[0] = lr_out<OutT>(GNX_SUB(1.0, p));
+        out[1] = lr_out<OutT>(p);
         return;
     }
     double p[APAD];
@@ -95,7 +111,7 @@ __device__ __forceinline__ void lr_epilogue_store(const int32_t (&acc)[LR_NCOLS]
     }
 #pragma unroll
     for (int a = 0; a < APAD; a++)
-        if (a < m.A) out[a] = (OutT)GNX_DIV(p[a], s);
+        if (a < m.A) out[a] = lr_out<OutT>(GNX_DIV(p[a], s));
 }
 
 }  // namespace gnx

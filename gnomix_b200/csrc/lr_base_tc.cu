@@ -6,7 +6,7 @@
 //   warp 1      MMA issuer: tcgen05.mma.kind::i8, M=128 (x2 haplotype halves), N=64, K=32,
 //               accumulators int32 in TMEM, 4 window slots of 128 columns
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: tcgen05.ld -> limb recombination (int64) -> float64 sigmoid /
+//   warps 4-19  epilogue (two groups of 8 warps on alternate windows): tcgen05.ld -> limb recombination (int64) -> float64 sigmoid /
 //               normalise -> B[n, w, :] (float32 or float64)
 // A CTA walks the SNP axis left to right for its 256 haplotypes; consecutive windows
 // overlap by 2*ctx SNPs, so each staged X chunk feeds the <= 4 windows that cover it
@@ -15,6 +15,8 @@
 // Replaces src/Base/base.py:146-180 + sklearn LogisticRegression.predict_proba
 // (src/Base/models.py:12-21).
 #include <cuda.h>
+
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -32,10 +34,12 @@ constexpr int SW = 8;
 constexpr int N_SLOTS = 4;
 constexpr int SLOT_COLS = 128;  // 2 halves x 64 columns
 constexpr int TMEM_COLS = 512;
-constexpr int N_THREADS = 384;
+constexpr int N_EPI_GROUPS = 2;  // epilogue groups take alternate windows (the float64 epilogue is latency-bound)
+constexpr int N_THREADS = 32 * (4 + 8 * N_EPI_GROUPS);
 constexpr int EPI_WARP0 = 4;
 constexpr int N_EPI_WARPS = 8;
-constexpr int SMEM_BYTES = 1024 + SX * X_STAGE_BYTES + SW * W_STAGE_BYTES + 256;
+constexpr int SMEM_BYTES = 1024 + SX * X_STAGE_BYTES + SW * W_STAGE_BYTES + 512;
+constexpr uint32_t META_END = 0xffffffffu;  // producer -> MMA issuer: no more tiles
 
 constexpr uint64_t HINT_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
@@ -71,6 +75,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         " [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -135,6 +149,7 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     uint64_t* acc_full = w_empty + SW;
     uint64_t* acc_empty = acc_full + N_SLOTS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + N_SLOTS);
+    volatile uint32_t* meta = tmem_slot + 4;  // [SW] per weight stage: slot | first<<2 | last<<3 | new_x<<4 | rel_x<<5
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -159,84 +174,117 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
     if (warp == 0) {
         // ---------------------------------------------------------- TMA producer
-        if (lane == 0) {
-            int xs = 0, ws = 0;
-            uint32_t xph = 0, wph = 0;
-            for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x) {
-                const int wblk = u / sc.n_htiles, ht = u - wblk * sc.n_htiles;
-                const int w_lo = wblk * sc.wb, w_hi = min(m.W, w_lo + sc.wb);
-                const int kb = __ldg(m.k0 + w_lo), ke = __ldg(m.kend + w_hi - 1);
-                const int hap0 = ht * TILE_HAPS;
-                for (int k = kb; k < ke; k++) {
-                    mbar_wait(&x_empty[xs], xph ^ 1);
+        // Warp-uniform loop, one elected lane issues; the per-chunk schedule (which windows cover
+        // the chunk, their weight tiles, first/last flags) is one 16-byte table entry.
+        int xs = 0, ws = 0;
+        uint32_t xph = 0, wph = 0;
+        uint32_t wbase = 0;  // running window counter of this CTA (TMEM slot = counter mod 4)
+        for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x) {
+            const int wblk = u / sc.n_htiles, ht = u - wblk * sc.n_htiles;
+            const int w_lo = wblk * sc.wb, w_hi = min(m.W, w_lo + sc.wb);
+            const int kb = __ldg(m.k0 + w_lo), ke = __ldg(m.kend + w_hi - 1);
+            const int hap0 = ht * TILE_HAPS;
+            uint4 sch = __ldg(m.chunk_sched + kb);
+            int cw0 = __ldg(m.chunk_w0 + kb);
+            for (int k = kb; k < ke; k++) {
+                mbar_wait(&x_empty[xs], xph ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&x_full[xs], X_STAGE_BYTES);
                     tma_load_2d(&tmX, &x_full[xs], smem_x + xs * X_STAGE_BYTES, k * LR_KC, hap0, HINT_EVICT_FIRST);
-                    if (++xs == SX) { xs = 0; xph ^= 1; }
-                    const int cw0 = __ldg(m.chunk_w0 + k);
-                    const int wa = max(cw0, w_lo), wz = min(cw0 + __ldg(m.chunk_wn + k), w_hi);
-                    for (int w = wa; w < wz; w++) {
-                        const int tile = __ldg(m.tile_off + w) + (k - __ldg(m.k0 + w));
-                        mbar_wait(&w_empty[ws], wph ^ 1);
-                        mbar_expect_tx(&w_full[ws], W_STAGE_BYTES);
-                        tma_load_2d(&tmW, &w_full[ws], smem_w + ws * W_STAGE_BYTES, 0, tile * LR_NCOLS, HINT_EVICT_LAST);
-                        if (++ws == SW) { ws = 0; wph ^= 1; }
+                }
+                __syncwarp();
+                if (++xs == SX) { xs = 0; xph ^= 1; }
+                const uint4 cur = sch;
+                const int c0 = cw0;
+                if (k + 1 < ke) {  // prefetch the next chunk's entry
+                    sch = __ldg(m.chunk_sched + k + 1);
+                    cw0 = __ldg(m.chunk_w0 + k + 1);
+                }
+                const uint32_t ent[4] = {cur.x, cur.y, cur.z, cur.w};
+                // windows of this block covering the chunk: indices [ia, iz) of the entry
+                const int ia = max(0, w_lo - c0);
+                int iz = min(4, w_hi - c0);
+#pragma unroll
+                for (int i = 3; i >= 0; i--)
+                    if (!(ent[i] & 4u) && iz > i) iz = i;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < ia || i >= iz) continue;
+                    const uint32_t e = ent[i];
+                    const uint32_t slot = (wbase + (uint32_t)(c0 + i - w_lo)) & (N_SLOTS - 1);
+                    const uint32_t mt = slot | ((e & 1u) << 2) | ((e & 2u) << 2) | ((i == ia) ? 16u : 0u) | ((i == iz - 1) ? 32u : 0u);
+                    mbar_wait(&w_empty[ws], wph ^ 1);
+                    if (elect_one()) {
+                        meta[ws] = mt;
+                        if (m.dbg & 4) {
+                            mbar_arrive(&w_full[ws]);
+                        } else {
+                            mbar_expect_tx(&w_full[ws], W_STAGE_BYTES);
+                            tma_load_2d(&tmW, &w_full[ws], smem_w + ws * W_STAGE_BYTES, 0, (int)(e >> 3) * LR_NCOLS, HINT_EVICT_LAST);
+                        }
                     }
+                    __syncwarp();
+                    if (++ws == SW) { ws = 0; wph ^= 1; }
                 }
             }
+            wbase += (uint32_t)(w_hi - w_lo);
+        }
+        mbar_wait(&w_empty[ws], wph ^ 1);
+        if (elect_one()) {
+            meta[ws] = META_END;
+            mbar_arrive(&w_full[ws]);
         }
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            // idesc: D=S32 (2<<4), A=S8 (1<<7), B=S8 (1<<10), K-major both, N=64 (8<<17), M=128 (8<<24)
-            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LR_NCOLS >> 3) << 17) | ((128u >> 4) << 24);
-            int xs = 0, ws = 0;
-            uint32_t xph = 0, wph = 0;
-            uint32_t wbase = 0;  // running window counter of this CTA
-            for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x) {
-                const int wblk = u / sc.n_htiles;
-                const int w_lo = wblk * sc.wb, w_hi = min(m.W, w_lo + sc.wb);
-                const int kb = __ldg(m.k0 + w_lo), ke = __ldg(m.kend + w_hi - 1);
-                for (int k = kb; k < ke; k++) {
-                    mbar_wait(&x_full[xs], xph);
-                    tc_fence_after();
-                    const uint32_t xaddr = smem_u32(smem_x + xs * X_STAGE_BYTES);
-                    const int cw0 = __ldg(m.chunk_w0 + k);
-                    const int wa = max(cw0, w_lo), wz = min(cw0 + __ldg(m.chunk_wn + k), w_hi);
-                    for (int w = wa; w < wz; w++) {
-                        const uint32_t widx = wbase + (uint32_t)(w - w_lo);
-                        const uint32_t slot = widx & (N_SLOTS - 1);
-                        const bool first = (k == __ldg(m.k0 + w));
-                        if (first) {
-                            mbar_wait(&acc_empty[slot], ((widx >> 2) & 1) ^ 1);
-                            tc_fence_after();
-                        }
-                        mbar_wait(&w_full[ws], wph);
-                        tc_fence_after();
-                        const uint32_t waddr = smem_u32(smem_w + ws * W_STAGE_BYTES);
+        // All 32 lanes run the loop with warp-uniform control flow and operands (so descriptor and
+        // address arithmetic stays on the uniform datapath); one elected lane issues the tcgen05
+        // instructions.  Everything the issuer needs to know about a weight stage (TMEM slot,
+        // first/last chunk of the window, first/last tile of the X chunk) comes from `meta`.
+        // idesc: D=S32 (2<<4), A=S8 (1<<7), B=S8 (1<<10), K-major both, N=64 (8<<17), M=128 (8<<24)
+        constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LR_NCOLS >> 3) << 17) | ((128u >> 4) << 24);
+        int xs = 0, ws = 0;
+        uint32_t xph = 0, wph = 0, slot_use = 0;  // bit s of slot_use: parity of the uses of TMEM slot s
+        const bool no_mma = (m.dbg & 1) != 0;
+        const uint32_t smem_x_u32 = smem_u32(smem_x), smem_w_u32 = smem_u32(smem_w);
+        for (;;) {
+            mbar_wait(&w_full[ws], wph);
+            const uint32_t mt = __shfl_sync(0xffffffffu, meta[ws], 0);
+            if (mt == META_END) break;
+            const uint32_t slot = mt & 3u;
+            const bool first = (mt & 4u) != 0;
+            if (mt & 16u) mbar_wait(&x_full[xs], xph);
+            if (first) {
+                mbar_wait(&acc_empty[slot], ((slot_use >> slot) & 1u) ^ 1u);
+                slot_use ^= 1u << slot;
+            }
+            tc_fence_after();
+            const uint64_t xdesc = make_desc(smem_x_u32 + xs * X_STAGE_BYTES);
+            const uint64_t wdesc = make_desc(smem_w_u32 + ws * W_STAGE_BYTES);
+            const uint32_t d0 = tmem_base + slot * SLOT_COLS;
+            if (elect_one()) {
+                if (!no_mma) {
 #pragma unroll
-                        for (int j = 0; j < LR_KC / 32; j++) {
-                            const uint64_t bdesc = make_desc(waddr + j * 32);
+                    for (int j = 0; j < LR_KC / 32; j++) {
 #pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                const uint64_t adesc = make_desc(xaddr + h * (128 * LR_KC) + j * 32);
-                                mma_i8(tmem_base + slot * SLOT_COLS + h * LR_NCOLS, adesc, bdesc, idesc, (first && j == 0) ? 0u : 1u);
-                            }
-                        }
-                        tc_commit(&w_empty[ws]);
-                        if (++ws == SW) { ws = 0; wph ^= 1; }
-                        if (k == __ldg(m.kend + w) - 1) tc_commit(&acc_full[slot]);
+                        for (int h = 0; h < 2; h++)
+                            mma_i8(d0 + h * LR_NCOLS, xdesc + (uint64_t)((h * (128 * LR_KC) + j * 32) >> 4), wdesc + (uint64_t)((j * 32) >> 4),
+                                   idesc, (first && j == 0) ? 0u : 1u);
                     }
-                    tc_commit(&x_empty[xs]);
-                    if (++xs == SX) { xs = 0; xph ^= 1; }
                 }
-                wbase += (uint32_t)(w_hi - w_lo);
+                tc_commit(&w_empty[ws]);
+                if (mt & 8u) tc_commit(&acc_full[slot]);
+                if (mt & 32u) tc_commit(&x_empty[xs]);
+            }
+            __syncwarp();
+            if (++ws == SW) { ws = 0; wph ^= 1; }
+            if (mt & 32u) {
+                if (++xs == SX) { xs = 0; xph ^= 1; }
             }
         }
-        __syncwarp();
     } else if (warp >= EPI_WARP0) {
         // -------------------------------------------------------------- epilogue
-        const int e = warp - EPI_WARP0;
+        const int e = (warp - EPI_WARP0) & 7, grp = (warp - EPI_WARP0) >> 3;
         const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
         const int half = e >> 2;
         uint32_t wbase = 0;
@@ -246,6 +294,7 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             const int64_t n = (int64_t)ht * TILE_HAPS + half * 128 + quad * 32 + lane;
             for (int w = w_lo; w < w_hi; w++) {
                 const uint32_t widx = wbase + (uint32_t)(w - w_lo);
+                if ((int)(widx % N_EPI_GROUPS) != grp) continue;
                 const uint32_t slot = widx & (N_SLOTS - 1);
                 mbar_wait(&acc_full[slot], (widx >> 2) & 1);
                 tc_fence_after();
@@ -257,7 +306,14 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[slot]);
-                if (n < N) lr_epilogue_store<APAD, OutT>(acc, m, w, B + (n * m.W + w) * m.A);
+                if (n < N && !(m.dbg & 2)) {
+                    if (m.dbg & 16) {  // profiling: stores only
+                        OutT* o = B + (n * m.W + w) * m.A;
+                        for (int a = 0; a < m.A; a++) o[a] = (OutT)acc[a];
+                    } else {
+                        lr_epilogue_store<APAD, OutT>(acc, m, w, B + (n * m.W + ((m.dbg & 8) ? 0 : w)) * m.A);
+                    }
+                }
             }
             wbase += (uint32_t)(w_hi - w_lo);
         }
@@ -358,6 +414,10 @@ int lr_launch_tc(const gnx_lr* mc, const int8_t* X, int64_t N, int64_t ldX, void
     if (tc::make_map_u8_2d(&tmX, X, (uint64_t)m->d.C, (uint64_t)N, (uint64_t)ldX, LR_KC, tc::TILE_HAPS)) return 1;
     const int sms = sm_count();
     GNX_REQUIRE(sms > 0, "no SMs?");
+    {
+        const char* e = getenv("GNX_LR_DBG");
+        m->d.dbg = e ? atoi(e) : 0;
+    }
     const tc::Sched sc = choose_sched(m, N, sms);
     const int grid = std::min(sms, sc.n_units);
     const CUtensorMap& tmW = *reinterpret_cast<const CUtensorMap*>(m->tmap_w);

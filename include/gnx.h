@@ -41,6 +41,10 @@ int gnx_version(void);
 const char* gnx_last_error(void);
 /* number of visible CUDA devices with compute capability 10.x; 0 if none */
 int gnx_device_count(void);
+/* Device self-test of the exact math helpers of gnx_math.h (division, int64->double,
+ * double<->float, exp range reduction) against the builtin IEEE operations over n random
+ * operand sets; mismatches[0..4] (host) receive the number of differing results. */
+int gnx_selftest_math(int64_t n, uint64_t seed, int64_t* mismatches);
 
 /* ---------------------------------------------------------------------------
  * K1  LogisticRegressionBase.predict_proba for all W windows
