@@ -2,9 +2,12 @@
 //
 // One persistent, warp-specialised CTA per SM:
 //   warp 0      TMA producer: X chunk [256 haplotypes x 128 SNPs] int8 (32 KB, 128B swizzle)
-//               + one weight tile [64 limb columns x 128 SNPs] per window covering the chunk
-//   warp 1      MMA issuer: tcgen05.mma.kind::i8, M=128 (x2 haplotype halves), N=64, K=32,
-//               accumulators int32 in TMEM, 4 window slots of 128 columns
+//               + one weight tile [64 limb columns x 128 SNPs] per window covering the chunk,
+//               placed in slot order inside a 32 KB weight stage
+//   warp 1      MMA issuer: tcgen05.mma.kind::i8, M=128 (x2 haplotype halves), K=32, N=64 per
+//               window -- the windows covering a chunk sit in consecutive TMEM slots and are
+//               issued as ONE instruction of N = 64..256 so the X tile is read from shared
+//               memory once per step; accumulators int32 in TMEM, 2 halves x 4 slots x 64 columns
 //   warp 2      TMEM allocator
 //   warps 4-19  epilogue (two groups of 8 warps on alternate windows): tcgen05.ld -> limb recombination (int64) -> float64 sigmoid /
 //               normalise -> B[n, w, :] (float32 or float64)
@@ -28,18 +31,19 @@ namespace tc {
 
 constexpr int TILE_HAPS = 256;
 constexpr int X_STAGE_BYTES = TILE_HAPS * LR_KC;  // 32 KB
-constexpr int W_STAGE_BYTES = LR_TILE_BYTES;      // 8 KB
+constexpr int N_SLOTS = 4;                         // live windows (TMEM accumulator slots)
+constexpr int W_TILE_BYTES = LR_TILE_BYTES;        // 8 KB: one window's weights for one chunk
+constexpr int W_STAGE_BYTES = N_SLOTS * W_TILE_BYTES;  // 32 KB: the weights of every window covering a chunk, in slot order
 constexpr int SX = 4;
-constexpr int SW = 8;
-constexpr int N_SLOTS = 4;
-constexpr int SLOT_COLS = 128;  // 2 halves x 64 columns
+constexpr int SW = 3;
+constexpr int HALF_COLS = N_SLOTS * LR_NCOLS;      // TMEM columns of one haplotype half: 4 slots x 64
 constexpr int TMEM_COLS = 512;
 constexpr int N_EPI_GROUPS = 2;  // epilogue groups take alternate windows (the float64 epilogue is latency-bound)
 constexpr int N_THREADS = 32 * (4 + 8 * N_EPI_GROUPS);
 constexpr int EPI_WARP0 = 4;
 constexpr int N_EPI_WARPS = 8;
 constexpr int SMEM_BYTES = 1024 + SX * X_STAGE_BYTES + SW * W_STAGE_BYTES + 512;
-constexpr uint32_t META_END = 0xffffffffu;  // producer -> MMA issuer: no more tiles
+constexpr uint32_t META_END = 0xffffffffu;  // producer -> MMA issuer: no more chunks
 
 constexpr uint64_t HINT_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
@@ -149,7 +153,8 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     uint64_t* acc_full = w_empty + SW;
     uint64_t* acc_empty = acc_full + N_SLOTS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + N_SLOTS);
-    volatile uint32_t* meta = tmem_slot + 4;  // [SW] per weight stage: slot | first<<2 | last<<3 | new_x<<4 | rel_x<<5
+    // per weight stage: first slot | n windows << 2 | first-chunk mask << 5 | last-chunk mask << 9
+    volatile uint32_t* meta = tmem_slot + 4;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -174,8 +179,10 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
     if (warp == 0) {
         // ---------------------------------------------------------- TMA producer
-        // Warp-uniform loop, one elected lane issues; the per-chunk schedule (which windows cover
-        // the chunk, their weight tiles, first/last flags) is one 16-byte table entry.
+        // Warp-uniform loop, one elected lane issues.  Per 128-SNP chunk: the X tile (256
+        // haplotypes x 128 SNPs) and, into one weight stage, the tile of every window that covers
+        // the chunk, each at the position of its TMEM slot so that windows in consecutive slots
+        // form one contiguous B operand.  The per-chunk schedule is one 16-byte table entry.
         int xs = 0, ws = 0;
         uint32_t xph = 0, wph = 0;
         uint32_t wbase = 0;  // running window counter of this CTA (TMEM slot = counter mod 4)
@@ -207,25 +214,27 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
                 for (int i = 3; i >= 0; i--)
                     if (!(ent[i] & 4u) && iz > i) iz = i;
+                const uint32_t slot0 = (wbase + (uint32_t)(c0 + ia - w_lo)) & (N_SLOTS - 1);
+                uint32_t mt = slot0 | ((uint32_t)(iz - ia) << 2);
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i < ia || i >= iz) continue;
-                    const uint32_t e = ent[i];
-                    const uint32_t slot = (wbase + (uint32_t)(c0 + i - w_lo)) & (N_SLOTS - 1);
-                    const uint32_t mt = slot | ((e & 1u) << 2) | ((e & 2u) << 2) | ((i == ia) ? 16u : 0u) | ((i == iz - 1) ? 32u : 0u);
-                    mbar_wait(&w_empty[ws], wph ^ 1);
-                    if (elect_one()) {
-                        meta[ws] = mt;
-                        if (m.dbg & 4) {
-                            mbar_arrive(&w_full[ws]);
-                        } else {
-                            mbar_expect_tx(&w_full[ws], W_STAGE_BYTES);
-                            tma_load_2d(&tmW, &w_full[ws], smem_w + ws * W_STAGE_BYTES, 0, (int)(e >> 3) * LR_NCOLS, HINT_EVICT_LAST);
-                        }
+                for (int i = 0; i < 4; i++)
+                    if (i >= ia && i < iz) mt |= ((ent[i] & 1u) << (5 + i - ia)) | (((ent[i] >> 1) & 1u) << (9 + i - ia));
+                mbar_wait(&w_empty[ws], wph ^ 1);
+                if (elect_one()) {
+                    meta[ws] = mt;
+                    if (m.dbg & 4) {
+                        mbar_arrive(&w_full[ws]);
+                    } else {
+                        mbar_expect_tx(&w_full[ws], (uint32_t)(iz - ia) * W_TILE_BYTES);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            if (i >= ia && i < iz)
+                                tma_load_2d(&tmW, &w_full[ws], smem_w + ws * W_STAGE_BYTES + ((slot0 + i - ia) & (N_SLOTS - 1)) * W_TILE_BYTES, 0,
+                                            (int)(ent[i] >> 3) * LR_NCOLS, HINT_EVICT_LAST);
                     }
-                    __syncwarp();
-                    if (++ws == SW) { ws = 0; wph ^= 1; }
                 }
+                __syncwarp();
+                if (++ws == SW) { ws = 0; wph ^= 1; }
             }
             wbase += (uint32_t)(w_hi - w_lo);
         }
@@ -237,12 +246,13 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        // All 32 lanes run the loop with warp-uniform control flow and operands (so descriptor and
+        // All 32 lanes run the loop with warp-uniform control flow and operands (descriptor and
         // address arithmetic stays on the uniform datapath); one elected lane issues the tcgen05
-        // instructions.  Everything the issuer needs to know about a weight stage (TMEM slot,
-        // first/last chunk of the window, first/last tile of the X chunk) comes from `meta`.
-        // idesc: D=S32 (2<<4), A=S8 (1<<7), B=S8 (1<<10), K-major both, N=64 (8<<17), M=128 (8<<24)
-        constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LR_NCOLS >> 3) << 17) | ((128u >> 4) << 24);
+        // instructions.  Per chunk and 32-SNP step the windows in consecutive TMEM slots with the
+        // same accumulate flag are ONE instruction of N = 64 x (windows): the X tile is fetched
+        // from shared memory once for all of them.
+        // idesc: D=S32 (2<<4), A=S8 (1<<7), B=S8 (1<<10), K-major both, M=128 (8<<24); N added per instruction
+        constexpr uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
         int xs = 0, ws = 0;
         uint32_t xph = 0, wph = 0, slot_use = 0;  // bit s of slot_use: parity of the uses of TMEM slot s
         const bool no_mma = (m.dbg & 1) != 0;
@@ -251,36 +261,46 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             mbar_wait(&w_full[ws], wph);
             const uint32_t mt = __shfl_sync(0xffffffffu, meta[ws], 0);
             if (mt == META_END) break;
-            const uint32_t slot = mt & 3u;
-            const bool first = (mt & 4u) != 0;
-            if (mt & 16u) mbar_wait(&x_full[xs], xph);
-            if (first) {
-                mbar_wait(&acc_empty[slot], ((slot_use >> slot) & 1u) ^ 1u);
-                slot_use ^= 1u << slot;
-            }
+            const uint32_t slot0 = mt & 3u, nwin = (mt >> 2) & 7u, fmask = (mt >> 5) & 15u, lmask = (mt >> 9) & 15u;
+            mbar_wait(&x_full[xs], xph);
+            for (uint32_t i = 0; i < nwin; i++)
+                if ((fmask >> i) & 1u) {
+                    const uint32_t slot = (slot0 + i) & (N_SLOTS - 1);
+                    mbar_wait(&acc_empty[slot], ((slot_use >> slot) & 1u) ^ 1u);
+                    slot_use ^= 1u << slot;
+                }
             tc_fence_after();
             const uint64_t xdesc = make_desc(smem_x_u32 + xs * X_STAGE_BYTES);
             const uint64_t wdesc = make_desc(smem_w_u32 + ws * W_STAGE_BYTES);
-            const uint32_t d0 = tmem_base + slot * SLOT_COLS;
             if (elect_one()) {
                 if (!no_mma) {
 #pragma unroll
                     for (int j = 0; j < LR_KC / 32; j++) {
+                        // segments of windows [i0, i1): consecutive slots without wrap, same accumulate flag
+                        uint32_t i0 = 0;
+                        while (i0 < nwin) {
+                            const uint32_t s0 = (slot0 + i0) & (N_SLOTS - 1);
+                            const uint32_t acc0 = (j == 0 && ((fmask >> i0) & 1u)) ? 0u : 1u;
+                            uint32_t i1 = i0 + 1;
+                            while (i1 < nwin && s0 + (i1 - i0) < N_SLOTS && ((j == 0 && ((fmask >> i1) & 1u)) ? 0u : 1u) == acc0) i1++;
+                            const uint32_t idesc = idesc0 | (((i1 - i0) * LR_NCOLS >> 3) << 17);
+                            const uint64_t bdesc = wdesc + (uint64_t)((s0 * W_TILE_BYTES + j * 32) >> 4);
 #pragma unroll
-                        for (int h = 0; h < 2; h++)
-                            mma_i8(d0 + h * LR_NCOLS, xdesc + (uint64_t)((h * (128 * LR_KC) + j * 32) >> 4), wdesc + (uint64_t)((j * 32) >> 4),
-                                   idesc, (first && j == 0) ? 0u : 1u);
+                            for (int h = 0; h < 2; h++)
+                                mma_i8(tmem_base + h * HALF_COLS + s0 * LR_NCOLS, xdesc + (uint64_t)((h * (128 * LR_KC) + j * 32) >> 4), bdesc,
+                                       idesc, acc0);
+                            i0 = i1;
+                        }
                     }
                 }
                 tc_commit(&w_empty[ws]);
-                if (mt & 8u) tc_commit(&acc_full[slot]);
-                if (mt & 32u) tc_commit(&x_empty[xs]);
+                tc_commit(&x_empty[xs]);
+                for (uint32_t i = 0; i < nwin; i++)
+                    if ((lmask >> i) & 1u) tc_commit(&acc_full[(slot0 + i) & (N_SLOTS - 1)]);
             }
             __syncwarp();
             if (++ws == SW) { ws = 0; wph ^= 1; }
-            if (mt & 32u) {
-                if (++xs == SX) { xs = 0; xph ^= 1; }
-            }
+            if (++xs == SX) { xs = 0; xph ^= 1; }
         }
     } else if (warp >= EPI_WARP0) {
         // -------------------------------------------------------------- epilogue
@@ -299,21 +319,14 @@ lr_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 mbar_wait(&acc_full[slot], (widx >> 2) & 1);
                 tc_fence_after();
                 int32_t acc[LR_NCOLS];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * SLOT_COLS + half * LR_NCOLS;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + half * HALF_COLS + slot * LR_NCOLS;
                 tmem_ld32(taddr, acc);
                 tmem_ld32(taddr + 32, acc + 32);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[slot]);
-                if (n < N && !(m.dbg & 2)) {
-                    if (m.dbg & 16) {  // profiling: stores only
-                        OutT* o = B + (n * m.W + w) * m.A;
-                        for (int a = 0; a < m.A; a++) o[a] = (OutT)acc[a];
-                    } else {
-                        lr_epilogue_store<APAD, OutT>(acc, m, w, B + (n * m.W + ((m.dbg & 8) ? 0 : w)) * m.A);
-                    }
-                }
+                if (n < N && !(m.dbg & 2)) lr_epilogue_store<APAD, OutT>(acc, m, w, B + (n * m.W + w) * m.A);
             }
             wbase += (uint32_t)(w_hi - w_lo);
         }
