@@ -157,6 +157,7 @@ def run_reference(args):
         return
     from gnomix_b200 import synth
     from oracle import c_oracle as co
+    co.use_all_cores()
     geom = synth.GEOMETRY[WORKLOAD]
     C, M, A, S, morgans = geom
     _, smooth, (fx, fpop), (coefs, icpts, ctx), forest_kind = build_models(geom)
@@ -285,6 +286,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import c_oracle as co
+        co.use_all_cores()
         ns = min(N, args.cpu_haps)
         Xs = X[:ns, :C].cpu().numpy()
         v, n_used, dt = time_cpu(Xs, coefs, icpts, geom, ctx, smooth.model)

@@ -45,6 +45,18 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline should use every host core."""
+    n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(n))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return num_threads()
+
+
 def pack_windows(arrs):
     """list of 2-D arrays -> (flat concat, int64 offsets)"""
     offs = np.zeros(len(arrs), dtype=np.int64)

@@ -30,6 +30,12 @@ int orc_num_threads(void) {
 #endif
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 double orc_exp(double x) { return gnx_exp(x); }
 float orc_expf_cr(float x) { return gnx_expf_cr(x); }
 
