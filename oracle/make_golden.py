@@ -220,21 +220,62 @@ def golden_gnofix(src):
 
 
 def golden_meta(src):
+    """get_meta_data + write_msp + write_fb (src/postprocess.py:25-126) on a small seeded case;
+    the written files are stored byte for byte."""
+    import tempfile
     import pandas as pd
-    from src.postprocess import get_meta_data
+    from src.postprocess import get_meta_data, write_msp, write_fb
     rng = np.random.default_rng(3)
-    C, M = 5231, 400
+    C, M, A = 5231, 400, 3
     W = C // M
+    n_ind = 4
     pos = np.sort(rng.choice(np.arange(16_000_000, 51_000_000), size=C, replace=False))
-    gpos = np.sort(rng.choice(np.arange(1000, 80_000), size=300, replace=False))
-    gen_map_df = pd.DataFrame({"chm": ["22"] * 300, "pos": np.sort(rng.choice(np.arange(15_000_000, 52_000_000), 300, replace=False)),
-                               "pos_cm": gpos / 1000.0})
-    meta = get_meta_data("22", pos, pos, W, M, gen_map_df)
-    np.savez_compressed(os.path.join(OUT, "meta.npz"), C=C, M=M, W=W, pos=pos, gm_pos=gen_map_df["pos"].values,
-                        gm_cm=gen_map_df["pos_cm"].values, columns=np.array(list(meta.columns)),
-                        table=meta.values.astype(np.float64) if all(np.issubdtype(t, np.number) for t in meta.dtypes) else
-                        np.array(meta.values.tolist(), dtype=object).astype(str))
-    print("meta", meta.shape, list(meta.columns))
+    # query has a subset of the model SNPs plus a few extra positions
+    qpos = np.sort(np.concatenate([rng.choice(pos, size=C - 300, replace=False), rng.choice(np.arange(16_000_000, 51_000_000), 50)]))
+    gm_pos = np.sort(rng.choice(np.arange(17_000_000, 50_000_000), 300, replace=False))
+    gm_cm = np.sort(rng.random(300) * 70.0)
+    gen_map_df = pd.DataFrame({"chm": ["22"] * 300, "pos": gm_pos, "pos_cm": gm_cm})
+    meta = get_meta_data("22", pos, qpos, W, M, gen_map_df)
+    labels = rng.integers(0, A, size=(2 * n_ind, W))
+    proba = rng.dirichlet(np.ones(A), size=(2 * n_ind, W)).astype(np.float32)
+    pops = ["AFR", "EUR", "EAS"]
+    samples = ["S%d" % i for i in range(n_ind)]
+    with tempfile.TemporaryDirectory() as td:
+        write_msp(os.path.join(td, "q"), meta, labels, pops, samples)
+        write_fb(os.path.join(td, "q"), meta, proba, pops, samples)
+        msp_bytes = open(os.path.join(td, "q.msp"), "rb").read()
+        fb_bytes = open(os.path.join(td, "q.fb"), "rb").read()
+    np.savez_compressed(os.path.join(OUT, "meta.npz"), C=C, M=M, W=W, A=A, pos=pos, qpos=qpos, gm_pos=gm_pos, gm_cm=gm_cm,
+                        columns=np.array(list(meta.columns)), table=np.asarray(meta.values).astype(str),
+                        labels=labels, proba=proba, pops=np.array(pops), samples=np.array(samples),
+                        msp=np.frombuffer(msp_bytes, dtype=np.uint8), fb=np.frombuffer(fb_bytes, dtype=np.uint8))
+    print("meta", meta.shape, list(meta.columns), len(msp_bytes), len(fb_bytes))
+
+
+def golden_vcf_to_npy(src):
+    """vcf_to_npy / snp_intersection (src/utils.py:83-159): pure numpy, driven with a
+    read_vcf-shaped dict (scikit-allel itself is not installable here)."""
+    from src.utils import vcf_to_npy
+    rng = np.random.default_rng(8)
+    n_ind, Cm = 5, 400
+    model_pos = np.sort(rng.choice(np.arange(1000, 90000), Cm, replace=False))
+    model_ref = rng.choice(np.array(["A", "C", "G", "T"]), Cm)
+    keep = np.sort(rng.choice(Cm, 330, replace=False))
+    extra = np.setdiff1d(rng.choice(np.arange(1000, 90000), 40), model_pos)
+    vpos = np.concatenate([model_pos[keep], extra])
+    vref = np.concatenate([model_ref[keep], rng.choice(np.array(["A", "C", "G", "T"]), len(extra))])
+    flip = rng.random(len(keep)) < 0.1
+    vref[:len(keep)][flip] = "N"
+    order = np.argsort(vpos)
+    vpos, vref = vpos[order], vref[order]
+    gt = rng.integers(0, 2, size=(len(vpos), n_ind, 2)).astype(np.int8)
+    gt[rng.random(gt.shape) < 0.02] = -1
+    vcf = {"calldata/GT": gt, "variants/POS": vpos, "variants/REF": vref}
+    X = vcf_to_npy(vcf, model_pos, model_ref, verbose=False)
+    X0 = vcf_to_npy({"calldata/GT": gt.copy(), "variants/POS": vpos, "variants/REF": vref}, None, None, verbose=False)
+    np.savez_compressed(os.path.join(OUT, "vcf_to_npy.npz"), gt=gt, vpos=vpos, vref=vref, model_pos=model_pos, model_ref=model_ref,
+                        X=X, X_noformat=X0)
+    print("vcf_to_npy", X.shape, X.dtype, np.bincount(X.ravel()))
 
 
 def main():
@@ -247,10 +288,8 @@ def main():
     golden_slide_window(src)
     golden_covrsk(src)
     golden_gnofix(src)
-    try:
-        golden_meta(src)
-    except Exception as e:  # get_meta_data is a "next" row; do not block the rest
-        print("meta skipped:", repr(e))
+    golden_meta(src)
+    golden_vcf_to_npy(src)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,106 @@
+"""CPU tests of the rows next to the hot path: window table, .msp/.fb writers,
+VCF -> int8 block -- against files and arrays produced by the reference's own functions."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _gen_map(d):
+    import pandas as pd
+    return pd.DataFrame({"chm": ["22"] * len(d["gm_pos"]), "pos": d["gm_pos"], "pos_cm": d["gm_cm"]})
+
+
+def test_meta_table_and_writers_byte_identical(tmp_path):
+    from gnomix_b200 import postprocess as pp
+    d = np.load(os.path.join(G, "meta.npz"))
+    meta = pp.get_meta_data("22", d["pos"], d["qpos"], int(d["W"]), int(d["M"]), _gen_map(d))
+    assert list(meta.columns) == d["columns"].tolist()
+    assert np.array_equal(np.asarray(meta.values).astype(str), d["table"])
+    pops, samples = d["pops"].tolist(), d["samples"].tolist()
+    pp.write_msp(str(tmp_path / "q"), meta, d["labels"], pops, samples)
+    pp.write_fb(str(tmp_path / "q"), meta, d["proba"], pops, samples)
+    assert open(tmp_path / "q.msp", "rb").read() == d["msp"].tobytes()
+    assert open(tmp_path / "q.fb", "rb").read() == d["fb"].tobytes()
+
+
+def test_meta_demo_known_answer():
+    """demo chr22 .msp geometry -- 370 windows of 857 SNPs."""
+    from gnomix_b200 import postprocess as pp
+    import pandas as pd
+    rng = np.random.default_rng(0)
+    C, M = 317_408, 857
+    pos = np.sort(rng.choice(np.arange(16_050_000, 51_240_000), C, replace=False))
+    gm = pd.DataFrame({"chm": ["22"] * 1000, "pos": np.linspace(16e6, 51.3e6, 1000).astype(int), "pos_cm": np.linspace(0, 74.1, 1000)})
+    meta = pp.get_meta_data("22", pos, pos, C // M, M, gm)
+    assert meta.shape == (370, 6)
+    n = np.asarray(meta["n snps"]).astype(float).astype(int)
+    assert n[:-1].tolist() == [857] * 369 and n[-1] == C - 857 * 369 and n.sum() == C
+    assert int(meta["spos"].iloc[0]) == pos[0] and int(meta["epos"].iloc[-1]) == pos[-1]
+
+
+def test_vcf_to_npy_against_reference():
+    from gnomix_b200 import io as gio
+    d = np.load(os.path.join(G, "vcf_to_npy.npz"))
+    vcf = {"calldata/GT": d["gt"].copy(), "variants/POS": d["vpos"], "variants/REF": d["vref"]}
+    X = gio.vcf_to_npy(vcf, d["model_pos"], d["model_ref"], verbose=False)
+    assert X.dtype == np.int8 and np.array_equal(X, d["X"])
+    X0 = gio.vcf_to_npy({"calldata/GT": d["gt"].copy(), "variants/POS": d["vpos"], "variants/REF": d["vref"]}, verbose=False)
+    assert np.array_equal(X0, d["X_noformat"])
+
+
+VCF_TEXT = """##fileformat=VCFv4.2
+##contig=<ID=22>
+#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\tS3
+22\t100\trs1\tA\tG\t.\tPASS\t.\tGT\t0|1\t1|1\t0|0
+22\t250\trs2\tC\tT\t.\tPASS\t.\tGT\t1|0\t.|.\t0|1
+21\t300\trs3\tG\tA\t.\tPASS\t.\tGT\t1|1\t1|1\t1|1
+22\t900\trs4\tT\tC\t.\tPASS\t.\tGT:DS\t0|0:0.1\t1|0:1.0\t1/1:2.0
+"""
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_read_vcf_small(tmp_path, gz):
+    from gnomix_b200 import io as gio
+    path = str(tmp_path / ("q.vcf.gz" if gz else "q.vcf"))
+    if gz:
+        with gzip.open(path, "wt") as f:
+            f.write(VCF_TEXT)
+    else:
+        open(path, "w").write(VCF_TEXT)
+    v = gio.read_vcf(path, chm="22")
+    assert v["samples"].tolist() == ["S1", "S2", "S3"]
+    assert v["variants/POS"].tolist() == [100, 250, 900]
+    assert v["variants/REF"].tolist() == ["A", "C", "T"] and v["variants/ALT"][:, 0].tolist() == ["G", "T", "C"]
+    assert v["variants/CHROM"].tolist() == ["22"] * 3
+    gt = v["calldata/GT"]
+    assert gt.shape == (3, 3, 2) and gt.dtype == np.int8
+    assert gt[0].tolist() == [[0, 1], [1, 1], [0, 0]]
+    assert gt[1].tolist() == [[1, 0], [-1, -1], [0, 1]]
+    assert gt[2].tolist() == [[0, 0], [1, 0], [1, 1]]
+    # region that does not exist -> the reference falls back to the whole file
+    assert len(gio.read_vcf(path, chm="7")["variants/POS"]) == 4
+    X = gio.vcf_to_npy(v, np.array([100, 250, 500, 900]), np.array(["A", "T", "G", "T"]), verbose=False)
+    assert X.tolist() == [[0, 0, 2, 0], [1, 1, 2, 0], [1, 2, 2, 1], [1, 2, 2, 0], [0, 1, 2, 1], [0, 0, 2, 1]]
+
+
+def test_read_vcf_demo_if_present():
+    from gnomix_b200 import io as gio
+    path = "/root/reference/demo/data/small_query_chr22.vcf.gz"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    v = gio.read_vcf(path, chm="22")
+    assert v["calldata/GT"].shape == (317_408, 9, 2)
+    assert set(np.unique(v["calldata/GT"]).tolist()) <= {0, 1}
+    assert v["variants/POS"][0] == 16_050_075 or v["variants/POS"][0] > 16_000_000
+
+
+def test_genetic_map_reader(tmp_path):
+    from gnomix_b200 import io as gio
+    p = tmp_path / "m.gmap"
+    p.write_text("chr22\t100\t0.0\nchr22\t200\t0.5\nchr1\t10\t0.1\n")
+    df = gio.read_genetic_map(str(p), chm="22")
+    assert df["pos"].tolist() == [100, 200] and df["pos_cm"].tolist() == [0.0, 0.5]
