@@ -96,6 +96,12 @@ class Gnomix:
         B_t2 = self.base.predict_proba(X_t2)
         self.smooth.train(B_t2, y_t2)
 
+        if self.calibrate:  # src/model.py:118-123: calibrated w.r.t. the train1 class distribution
+            if verbose:
+                print("Fitting calibrator...")
+            B_t1 = self.base.predict_proba(X_t1)
+            self.smooth.train_calibrator(B_t1, y_t1)
+
         if evaluate:
             if verbose:
                 print("Evaluating model...")

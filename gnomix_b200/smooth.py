@@ -95,6 +95,21 @@ class Smoother:
         return accr, accr_bal
 
 
+def _train_calibrator(self, B, y, frac=0.05):
+    """src/Smooth/smooth.py:81-92."""
+    from .calibration import Calibrator
+    calibrate = self.calibrate
+    self.calibrate = False
+    idxs = np.random.choice(len(B), int(frac * len(B)), replace=False)
+    proba = np.asarray(self.predict_proba(np.asarray(B)[idxs])).reshape(-1, self.A)
+    self.calibrate = calibrate
+    self.calibrator = Calibrator(self.A)
+    self.calibrator.fit(proba, np.asarray(y)[idxs].reshape(-1))
+
+
+Smoother.train_calibrator = _train_calibrator
+
+
 def host_slide_window(B, S):
     """Training-time twin of slide_window (src/Smooth/utils.py:4-29): only Smoother.train
     needs the materialised matrix (on a subsample), inference never does."""

@@ -165,3 +165,49 @@ def test_two_rank_scatter_gather_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in ps]
     assert all(p.returncode == 0 for p in ps), outs
     assert "OK" in outs[0]
+
+
+def test_calibrator_matches_reference_semantics():
+    """Calibrator.fit/transform (src/Smooth/Calibration.py:19-69): per-class isotonic regression,
+    renormalise, NaN -> 1/A, clip tiny overshoot."""
+    from sklearn.isotonic import IsotonicRegression
+    from gnomix_b200.calibration import Calibrator
+    rng = np.random.default_rng(0)
+    A = 4
+    y = rng.integers(0, A, 3000)
+    proba = rng.dirichlet(np.ones(A), 3000).astype(np.float32)
+    proba[np.arange(3000), y] += 0.5
+    proba /= proba.sum(1, keepdims=True)
+    cal = Calibrator(A)
+    cal.fit(proba, y)
+    test = rng.dirichlet(np.ones(A), (5, 40)).astype(np.float32)
+    out = cal.transform(test)
+    assert out.shape == test.shape
+    want = np.stack([IsotonicRegression(out_of_bounds="clip").fit(proba[:, i], (y == i).astype(float)).transform(test.reshape(-1, A)[:, i])
+                     for i in range(A)], axis=1)
+    with np.errstate(invalid="ignore"):
+        want /= want.sum(1, keepdims=True)
+    want[np.isnan(want)] = 1.0 / A
+    assert np.allclose(out.reshape(-1, A), want)
+    assert Calibrator(3).transform(test[..., :3]) is not None  # untrained: returns the input with a warning
+
+
+def test_crf_trainer_learns_sticky_chain():
+    from gnomix_b200.crf_train import fit_crf, crf_nll_grad
+    from oracle import np_oracle as npo
+    rng = np.random.default_rng(1)
+    A, N, W = 3, 60, 40
+    y = np.zeros((N, W), dtype=int)
+    for n in range(N):
+        cur = rng.integers(A)
+        for t in range(W):
+            if rng.random() < 0.05:
+                cur = rng.integers(A)
+            y[n, t] = cur
+    B = rng.dirichlet(np.ones(A) * 0.8, (N, W))
+    B[np.arange(N)[:, None], np.arange(W)[None, :], y] += 0.4
+    B /= B.sum(-1, keepdims=True)
+    sw, tw = fit_crf(B, y, A, max_iterations=80)
+    assert np.all(np.diag(tw) > tw.max(axis=1) - 1e-9)           # staying is the preferred transition
+    proba, lab = npo.crf_smooth(B, sw, tw)
+    assert (lab == y).mean() > (np.argmax(B, -1) == y).mean()    # smoothing beats the raw base argmax
