@@ -58,7 +58,7 @@ __device__ __forceinline__ int64_t svc_pad_to_orig(int64_t p, int64_t C, int64_t
 }
 
 // ------------------------------------------------------------------------------ K2
-// grid.x = ceil(N / 64).  Kt != NULL: Kt[s * ldK + n]; else Krow[n * nsv + s].
+// grid = (ceil(N / 64), ceil(nsv / 64)).  Kt != NULL: Kt[s * ldK + n]; else Krow[n * nsv + s].
 __global__ void __launch_bounds__(SVC_THREADS, 2)
 svc_kernel_window(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, int64_t ldX, int32_t* __restrict__ Kt, int64_t ldK,
                   int32_t* __restrict__ Krow) {
@@ -87,7 +87,8 @@ svc_kernel_window(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, i
     const uint32_t* q0a = qp + ((lane) * 2) * nwp;
     const uint32_t* q1a = qp + ((lane + 32) * 2) * nwp;
 
-    for (int s0 = 0; s0 < w.nsv; s0 += SVC_CHUNK) {
+    {   // one support-vector chunk per CTA (grid.y)
+        const int s0 = blockIdx.y * SVC_CHUNK;
         const int ns = min(SVC_CHUNK, w.nsv - s0);
         __syncthreads();
         {
@@ -434,7 +435,8 @@ static int svc_launch_kernel(const gnx_svc_t* m, int w, const int8_t* X, int64_t
         const size_t smem = ((size_t)SVC_Q * 2 * sw.nwp + (size_t)SVC_CHUNK * 2 * sw.nw) * 4;
         GNX_REQUIRE(smem <= 227 * 1024, "gnx_svc: window of %d SNPs too long for shared memory", sw.len);
         GNX_CUDA(cudaFuncSetAttribute(svc_kernel_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        svc_kernel_window<<<(unsigned)ceil_div(N, SVC_Q), SVC_THREADS, smem, st>>>(m->d, sw, X, N, ldX, Kt, ldK, Krow);
+        dim3 grid((unsigned)ceil_div(N, SVC_Q), (unsigned)ceil_div(sw.nsv, SVC_CHUNK));
+        svc_kernel_window<<<grid, SVC_THREADS, smem, st>>>(m->d, sw, X, N, ldX, Kt, ldK, Krow);
     } else {
         dim3 grid((unsigned)ceil_div(N, 128), (unsigned)sw.nsv);
         svc_kernel_window_generic<<<grid, 128, 0, st>>>(m->d, sw, X, N, ldX, Kt, ldK, Krow);
