@@ -309,6 +309,9 @@ def run_ours(args):
                                  "tree_traversals_per_s": N * W * smooth.model.n_trees / (k4_ms * 1e-3)},
     }
     dom = "K1_lr_tc_kernel" if k1_ms >= k4_ms else "K4_gbt_smooth_kernel"
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
+    # exact command (profiles/r1_ncu_final_summary.txt); only valid for the default workload size
+    traffic = {"K1_lr_tc_kernel": 68.05e9, "K4_gbt_smooth_kernel": 4.25e9} if (N == 50_000 and WORKLOAD == "chr1") else {}
     out = {
         "metric": "haplotypes/sec local-ancestry inference (Base->Smooth->argmax), chr1, 7-way",
         "value": value, "unit": "haplotypes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -324,7 +327,13 @@ def run_ours(args):
                 "api": "gnx_infer_host (pinned host int8 in, int32 labels out)", "labels_match_resident_path": labels_match},
         "gpu_launches": 2 * args.steps,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src},
+                     "frac": kernels[dom]["frac_hbm"], "traffic": traffic.get(dom), "peak_source": peak_src,
+                     "note": "the smoother (K4) dominates the step and is bound by issue slots / shared-memory wavefronts "
+                             "(ncu: issue-active 89 %, LSU shared wavefronts 80 % of peak), not by HBM; the HBM-bound kernel "
+                             "of the path is K1, see roofline_base"},
+        "roofline_base": {"kernel": "K1_lr_tc_kernel", "bound": "hbm", "achieved": kernels["K1_lr_tc_kernel"]["gbs"], "peak": peak,
+                          "unit": "GB/s", "frac": kernels["K1_lr_tc_kernel"]["frac_hbm"], "traffic": traffic.get("K1_lr_tc_kernel"),
+                          "peak_source": peak_src},
         "kernels": kernels,
         "clocks": clocks,
     }
