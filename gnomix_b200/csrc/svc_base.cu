@@ -31,7 +31,7 @@ namespace gnx {
 
 constexpr int SVC_MAX_A = 16;
 constexpr int SVC_Q = 64;        // query haplotypes per CTA
-constexpr int SVC_CHUNK = 64;    // support vectors staged per pass
+constexpr int SVC_CHUNK = 48;    // support vectors staged per CTA (3 CTAs per SM fit in shared memory)
 constexpr int SVC_THREADS = 256;
 
 struct SvcWin {
@@ -59,9 +59,10 @@ __device__ __forceinline__ int64_t svc_pad_to_orig(int64_t p, int64_t C, int64_t
 
 // ------------------------------------------------------------------------------ K2
 // grid = (ceil(N / 64), ceil(nsv / 64)).  Kt != NULL: Kt[s * ldK + n]; else Krow[n * nsv + s].
-__global__ void __launch_bounds__(SVC_THREADS, 2)
-svc_kernel_window(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, int64_t ldX, int32_t* __restrict__ Kt, int64_t ldK,
-                  int32_t* __restrict__ Krow) {
+template <int SM_T>
+__global__ void __launch_bounds__(SVC_THREADS, 3)
+svc_kernel_window(SvcDev m, SvcWin w, const uint32_t* __restrict__ QP, int64_t qp_words, int64_t N, int32_t* __restrict__ Kt,
+                  int64_t ldK, int32_t* __restrict__ Krow) {
     extern __shared__ __align__(16) uint32_t sm[];
     uint32_t* qp = sm;                               // [64][2][nwp]
     uint32_t* sp = sm + (size_t)SVC_Q * 2 * w.nwp;   // [SVC_CHUNK][2][nw]
@@ -69,18 +70,20 @@ svc_kernel_window(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, i
     const int64_t n0 = (int64_t)blockIdx.x * SVC_Q;
     const int nw = w.nw, nwp = w.nwp;
 
-    // ---- query bit planes: one warp per haplotype, 32 SNPs per ballot
-    for (int q = warp; q < SVC_Q; q += SVC_THREADS / 32) {
-        const int64_t n = n0 + q;
-        for (int j = 0; j < nw; j++) {
-            const int p = j * 32 + lane;
-            int v = 0;
-            if (n < N && p < w.len) v = X[n * ldX + svc_pad_to_orig(w.lo + p, m.C, m.ctx)];
-            const uint32_t b0 = __ballot_sync(0xffffffffu, v & 1), b1 = __ballot_sync(0xffffffffu, v & 2);
-            if (lane == 0) {
-                qp[(q * 2 + 0) * nwp + j] = b0;
-                qp[(q * 2 + 1) * nwp + j] = b1;
+    // ---- query bit planes of this window: an unaligned bit range of the packed padded planes
+    {
+        const int64_t wi0 = w.lo >> 5;
+        const int sh = (int)(w.lo & 31);
+        for (int i = threadIdx.x; i < SVC_Q * 2 * nw; i += SVC_THREADS) {
+            const int q = i / (2 * nw), rem = i - q * 2 * nw;
+            const int pl = rem / nw, j = rem - pl * nw;
+            const int64_t n = n0 + q;
+            uint32_t v = 0u;
+            if (n < N) {
+                const uint32_t* src = QP + ((size_t)n * 2 + pl) * qp_words + wi0 + j;
+                v = __funnelshift_r(__ldg(src), __ldg(src + 1), sh);
             }
+            qp[(q * 2 + pl) * nwp + j] = v;
         }
     }
     const uint32_t tail = (w.len & 31) ? ((1u << (w.len & 31)) - 1u) : 0xffffffffu;
@@ -96,15 +99,16 @@ svc_kernel_window(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, i
             for (int i = threadIdx.x; i < ns * 2 * nw; i += SVC_THREADS) sp[i] = __ldg(src + i);
         }
         __syncthreads();
-        // warp handles support vectors warp*8 .. warp*8+7 of the chunk, 4 at a time, x 2 queries per lane
-        for (int sb = warp * 8; sb < warp * 8 + 8 && sb < ns; sb += 4) {
-            int K[2][4];
-            uint32_t zp[2][4], r2p[2][4], r4p[2][4], r8p[2][4], r16p[2][4];
-            int run[2][4];
+        // warp handles support vectors warp*6 .. warp*6+5 of the chunk, 3 at a time, x 2 queries per lane
+        constexpr int SB = 3;
+        for (int sb = warp * (SVC_CHUNK / 8); sb < (warp + 1) * (SVC_CHUNK / 8) && sb < ns; sb += SB) {
+            int K[2][SB];
+            uint32_t zp[2][SB], r2p[2][SB], r4p[2][SB], r8p[2][SB], r16p[2][SB];
+            int run[2][SB];
 #pragma unroll
             for (int a = 0; a < 2; a++)
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
+                for (int b = 0; b < SB; b++) {
                     K[a][b] = 0;
                     zp[a][b] = r2p[a][b] = r4p[a][b] = r8p[a][b] = r16p[a][b] = 0u;
                     run[a][b] = 0;
@@ -115,41 +119,42 @@ svc_kernel_window(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, i
                 xq[1][0] = q1a[j]; xq[1][1] = q1a[nwp + j];
                 const uint32_t msk = (j == nw - 1) ? tail : 0xffffffffu;
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
+                for (int b = 0; b < SB; b++) {
                     const int s = min(sb + b, ns - 1);
                     const uint32_t y0 = sp[(s * 2 + 0) * nw + j], y1 = sp[(s * 2 + 1) * nw + j];
 #pragma unroll
                     for (int a = 0; a < 2; a++) {
+                        const int smask = (SM_T >= 0) ? SM_T : m.small_mask;
                         const uint32_t z = ~((xq[a][0] ^ y0) | (xq[a][1] ^ y1)) & msk;
                         int k = 0;
-                        if (m.small_mask & 1) k += __popc(z);
+                        if (smask & 1) k += __popc(z);
                         const uint32_t r2 = z & __funnelshift_l(zp[a][b], z, 1);
-                        if (m.small_mask & 2) k += __popc(r2);
+                        if (smask & 2) k += __popc(r2);
                         const uint32_t r4 = r2 & __funnelshift_l(r2p[a][b], r2, 2);
-                        if (m.small_mask & 4) k += __popc(r4);
+                        if (smask & 4) k += __popc(r4);
                         const uint32_t r8 = r4 & __funnelshift_l(r4p[a][b], r4, 4);
-                        if (m.small_mask & 8) k += __popc(r8);
-                        if (m.small_mask & 48) {
+                        if (smask & 8) k += __popc(r8);
+                        if (smask & 48) {
                             const uint32_t r16 = r8 & __funnelshift_l(r8p[a][b], r8, 8);
-                            if (m.small_mask & 16) k += __popc(r16);
-                            if (m.small_mask & 32) k += __popc(r16 & __funnelshift_l(r16p[a][b], r16, 16));
+                            if (smask & 16) k += __popc(r16);
+                            if (smask & 32) k += __popc(r16 & __funnelshift_l(r16p[a][b], r16, 16));
                             r16p[a][b] = r16;
                         }
                         zp[a][b] = z; r2p[a][b] = r2; r4p[a][b] = r4; r8p[a][b] = r8;
-                        // maximal runs longer than 32 (they cross a word boundary)
-                        if (z == 0xffffffffu) {
-                            run[a][b] += 32;
-                        } else {
-                            const int L = run[a][b] + (__ffs(~z) - 1);
-                            if (L >= m.min_big) k += __ldg(m.gbig + L);
-                            run[a][b] = __clz(~z);
-                        }
+                        // maximal runs longer than 32 cross a word boundary: branch-free bookkeeping of the
+                        // run that is open at the top of the word; the table lookup only when a long run ends
+                        const uint32_t nz = ~z;
+                        const int t1 = __clz(__brev(nz));          // trailing ones (32 if the word is all ones)
+                        const int L = run[a][b] + t1;
+                        const bool open = (nz == 0u);
+                        if (!open && L >= m.min_big) k += __ldg(m.gbig + L);
+                        run[a][b] = open ? L : __clz(nz);          // leading ones carry into the next word
                         K[a][b] += k;
                     }
                 }
             }
 #pragma unroll
-            for (int b = 0; b < 4; b++)
+            for (int b = 0; b < SB; b++)
 #pragma unroll
                 for (int a = 0; a < 2; a++) {
                     int k = K[a][b];
@@ -161,6 +166,27 @@ svc_kernel_window(SvcDev m, SvcWin w, const int8_t* __restrict__ X, int64_t N, i
                         else Krow[n * w.nsv + s] = k;
                     }
                 }
+        }
+    }
+}
+
+// Bit planes of the reflect-padded haplotypes (src/Base/base.py:41-44), once per predict call:
+// QP[n][plane][word], bit b of word j = plane bit of padded column 32 j + b; one spare zero word.
+__global__ void svc_pack_kernel(SvcDev m, const int8_t* __restrict__ X, int64_t N, int64_t ldX, uint32_t* __restrict__ QP,
+                                int64_t qp_words) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t padded = m.C + 2 * m.ctx;
+    const int64_t total = N * qp_words;
+    for (int64_t t = warp; t < total; t += nwarps) {
+        const int64_t n = t / qp_words, j = t - n * qp_words;
+        const int64_t p = j * 32 + lane;
+        int v = 0;
+        if (p < padded) v = X[n * ldX + svc_pad_to_orig(p, m.C, m.ctx)];
+        const uint32_t b0 = __ballot_sync(0xffffffffu, v & 1), b1 = __ballot_sync(0xffffffffu, v & 2);
+        if (lane == 0) {
+            QP[((size_t)n * 2 + 0) * qp_words + j] = b0;
+            QP[((size_t)n * 2 + 1) * qp_words + j] = b1;
         }
     }
 }
@@ -232,9 +258,10 @@ __device__ void svc_multiclass_probability(int k, const double* r, double* p) {
     }
 }
 
-// thread = one haplotype; one pass over the support vectors in order feeds all pairwise sums
+// K3a: thread = one (haplotype, class pair): the pairwise decision value in libsvm's order (class i's
+// support vectors, then class j's), Platt sigmoid -> r_ij into R[p][n]
 __global__ void __launch_bounds__(128)
-svc_proba_window(SvcDev m, SvcWin w, int wi, const int32_t* __restrict__ Kt, int64_t ldK, int64_t N, double* __restrict__ B) {
+svc_pair_window(SvcDev m, SvcWin w, const int32_t* __restrict__ Kt, int64_t ldK, int64_t N, double* __restrict__ R) {
     __shared__ int s_start[SVC_MAX_A + 1];
     if (threadIdx.x == 0) {
         s_start[0] = 0;
@@ -242,37 +269,40 @@ svc_proba_window(SvcDev m, SvcWin w, int wi, const int32_t* __restrict__ Kt, int
     }
     __syncthreads();
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
+    if (n >= N) return;
+    // pair index p -> (i, j), i < j, libsvm order
+    int i = 0, rem = p;
+    while (rem >= m.A - 1 - i) { rem -= m.A - 1 - i; i++; }
+    const int j = i + 1 + rem;
+    double sum = 0.0;
+    const double* ci = w.coef + (size_t)(j - 1) * w.nsv;
+    const double* cj = w.coef + (size_t)i * w.nsv;
+    for (int s = s_start[i]; s < s_start[i + 1]; s++) sum += __ldg(ci + s) * (double)Kt[(int64_t)s * ldK + n];
+    for (int s = s_start[j]; s < s_start[j + 1]; s++) sum += __ldg(cj + s) * (double)Kt[(int64_t)s * ldK + n];
+    const double dec = sum + w.intercept[p];
+    const double fApB = dec * w.probA[p] + w.probB[p];
+    double v;
+    if (fApB >= 0)
+        v = gnx_exp(-fApB) / (1.0 + gnx_exp(-fApB));
+    else
+        v = 1.0 / (1 + gnx_exp(fApB));
+    if (v < 1e-7) v = 1e-7;
+    if (v > 1 - 1e-7) v = 1 - 1e-7;
+    R[(int64_t)p * ldK + n] = v;
+}
+
+// K3b: thread = one haplotype: pairwise coupling of the P pair probabilities
+__global__ void __launch_bounds__(128)
+svc_couple_window(SvcDev m, int wi, const double* __restrict__ R, int64_t ldK, int64_t N, double* __restrict__ B) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const int k = m.A;
-    double sum[SVC_MAX_A * (SVC_MAX_A - 1) / 2];
-    for (int p = 0; p < m.P; p++) sum[p] = 0.0;
-    // pair index of (i, j), i < j, in libsvm order
-    auto pidx = [k](int i, int j) { return i * k - i * (i + 1) / 2 + (j - i - 1); };
-    for (int c = 0; c < k; c++) {
-        for (int s = s_start[c]; s < s_start[c + 1]; s++) {
-            const double kv = (double)Kt[(int64_t)s * ldK + n];
-            for (int d = 0; d < k; d++) {
-                if (d == c) continue;
-                // class c plays "i" against d > c (coef row d-1) and "j" against d < c (coef row d)
-                const double cf = (d > c) ? __ldg(w.coef + (size_t)(d - 1) * w.nsv + s) : __ldg(w.coef + (size_t)d * w.nsv + s);
-                const int p = (d > c) ? pidx(c, d) : pidx(d, c);
-                sum[p] += cf * kv;
-            }
-        }
-    }
     double pair[SVC_MAX_A * SVC_MAX_A];
     int p = 0;
     for (int i = 0; i < k; i++)
         for (int j = i + 1; j < k; j++) {
-            const double dec = sum[p] + w.intercept[p];
-            const double fApB = dec * w.probA[p] + w.probB[p];
-            double v;
-            if (fApB >= 0)
-                v = gnx_exp(-fApB) / (1.0 + gnx_exp(-fApB));
-            else
-                v = 1.0 / (1 + gnx_exp(fApB));
-            if (v < 1e-7) v = 1e-7;
-            if (v > 1 - 1e-7) v = 1 - 1e-7;
+            const double v = R[(int64_t)p * ldK + n];
             pair[i * k + j] = v;
             pair[j * k + i] = 1 - v;
             p++;
@@ -427,16 +457,31 @@ void gnx_svc_model_destroy(gnx_svc_t* m) {
     delete m;
 }
 
-static int svc_launch_kernel(const gnx_svc_t* m, int w, const int8_t* X, int64_t N, int64_t ldX, int32_t* Kt, int64_t ldK, int32_t* Krow,
-                             cudaStream_t st) {
+static int64_t svc_qp_words(const gnx_svc_t* m) { return (m->d.C + 2 * m->d.ctx + 31) / 32 + 1; }
+
+static int svc_pack(const gnx_svc_t* m, const int8_t* X, int64_t N, int64_t ldX, uint32_t* QP, cudaStream_t st) {
+    const int64_t total_warps = N * svc_qp_words(m);
+    const int grid = (int)std::min<int64_t>(ceil_div(total_warps, 8), (int64_t)sm_count() * 16);
+    svc_pack_kernel<<<grid, 256, 0, st>>>(m->d, X, N, ldX, QP, svc_qp_words(m));
+    GNX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int svc_launch_kernel(const gnx_svc_t* m, int w, const int8_t* X, const uint32_t* QP, int64_t N, int64_t ldX, int32_t* Kt, int64_t ldK,
+                             int32_t* Krow, cudaStream_t st) {
     const SvcWin& sw = m->win[w];
     if (sw.nsv == 0) return 0;
     if (m->d.fast) {
         const size_t smem = ((size_t)SVC_Q * 2 * sw.nwp + (size_t)SVC_CHUNK * 2 * sw.nw) * 4;
         GNX_REQUIRE(smem <= 227 * 1024, "gnx_svc: window of %d SNPs too long for shared memory", sw.len);
-        GNX_CUDA(cudaFuncSetAttribute(svc_kernel_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GNX_CUDA(cudaFuncSetAttribute(svc_kernel_window<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)ceil_div(N, SVC_Q), (unsigned)ceil_div(sw.nsv, SVC_CHUNK));
-        svc_kernel_window<<<grid, SVC_THREADS, smem, st>>>(m->d, sw, X, N, ldX, Kt, ldK, Krow);
+        if (m->d.small_mask == 13) {  // lengths {1, 4, 8} below 33: every CovSample(., 0.6, 1.0, 37) list
+            GNX_CUDA(cudaFuncSetAttribute(svc_kernel_window<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            svc_kernel_window<13><<<grid, SVC_THREADS, smem, st>>>(m->d, sw, QP, svc_qp_words(m), N, Kt, ldK, Krow);
+        } else {
+            svc_kernel_window<-1><<<grid, SVC_THREADS, smem, st>>>(m->d, sw, QP, svc_qp_words(m), N, Kt, ldK, Krow);
+        }
     } else {
         dim3 grid((unsigned)ceil_div(N, 128), (unsigned)sw.nsv);
         svc_kernel_window_generic<<<grid, 128, 0, st>>>(m->d, sw, X, N, ldX, Kt, ldK, Krow);
@@ -451,7 +496,15 @@ int gnx_svc_kernel_window(const gnx_svc_t* m, int w, const int8_t* X_dev, int64_
     GNX_REQUIRE(N >= 0 && ldX >= m->d.C, "gnx_svc_kernel_window: bad shape");
     if (N == 0) return 0;
     GNX_REQUIRE(X_dev && K_dev, "gnx_svc_kernel_window: NULL buffer");
-    return svc_launch_kernel(m, w, X_dev, N, ldX, nullptr, 0, K_dev, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* QP = nullptr;
+    if (m->d.fast) {
+        GNX_CUDA(cudaMallocAsync((void**)&QP, sizeof(uint32_t) * (size_t)N * 2 * svc_qp_words(m), st));
+        if (svc_pack(m, X_dev, N, ldX, QP, st)) return 1;
+    }
+    const int rc = svc_launch_kernel(m, w, X_dev, QP, N, ldX, nullptr, 0, K_dev, st);
+    if (QP) cudaFreeAsync(QP, st);
+    return rc;
 }
 
 int gnx_svc_predict(const gnx_svc_t* m, const int8_t* X_dev, int64_t N, int64_t ldX, double* B_dev, void* stream) {
@@ -461,19 +514,28 @@ int gnx_svc_predict(const gnx_svc_t* m, const int8_t* X_dev, int64_t N, int64_t 
     GNX_REQUIRE(X_dev && B_dev, "gnx_svc_predict: NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t ldK = (N + 31) & ~int64_t(31);
-    int32_t* Kt = nullptr;
-    GNX_CUDA(cudaMallocAsync((void**)&Kt, sizeof(int32_t) * (size_t)std::max(1, m->max_nsv) * ldK, st));
+    const size_t kt_bytes = (sizeof(int32_t) * (size_t)std::max(1, m->max_nsv) * ldK + 255) & ~size_t(255);
+    const size_t r_bytes = (sizeof(double) * (size_t)m->d.P * ldK + 255) & ~size_t(255);
+    const size_t qp_bytes = m->d.fast ? sizeof(uint32_t) * (size_t)N * 2 * svc_qp_words(m) : 0;
+    char* scratch = nullptr;
+    GNX_CUDA(cudaMallocAsync((void**)&scratch, kt_bytes + r_bytes + qp_bytes + 256, st));
+    int32_t* Kt = reinterpret_cast<int32_t*>(scratch);
+    double* R = reinterpret_cast<double*>(scratch + kt_bytes);
+    uint32_t* QP = m->d.fast ? reinterpret_cast<uint32_t*>(scratch + kt_bytes + r_bytes) : nullptr;
     int rc = 0;
+    if (QP) rc = svc_pack(m, X_dev, N, ldX, QP, st);
     for (int w = 0; w < m->d.W && rc == 0; w++) {
-        rc = svc_launch_kernel(m, w, X_dev, N, ldX, Kt, ldK, nullptr, st);
+        rc = svc_launch_kernel(m, w, X_dev, QP, N, ldX, Kt, ldK, nullptr, st);
         if (rc) break;
-        svc_proba_window<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(m->d, m->win[w], w, Kt, ldK, N, B_dev);
+        dim3 gp((unsigned)ceil_div(N, 128), (unsigned)m->d.P);
+        svc_pair_window<<<gp, 128, 0, st>>>(m->d, m->win[w], Kt, ldK, N, R);
+        svc_couple_window<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(m->d, w, R, ldK, N, B_dev);
         if (cudaGetLastError() != cudaSuccess) {
             set_error("gnx_svc_predict: launch failed (window %d)", w);
             rc = 1;
         }
     }
-    cudaFreeAsync(Kt, st);
+    cudaFreeAsync(scratch, st);
     return rc;
 }
 
