@@ -211,3 +211,31 @@ def test_crf_trainer_learns_sticky_chain():
     assert np.all(np.diag(tw) > tw.max(axis=1) - 1e-9)           # staying is the preferred transition
     proba, lab = npo.crf_smooth(B, sw, tw)
     assert (lab == y).mean() > (np.argmax(B, -1) == y).mean()    # smoothing beats the raw base argmax
+
+
+def test_reference_import_paths_resolve_to_this_package():
+    """gnomix.py and the reference's pickles name these modules (gnomix.py:11-21)."""
+    import importlib
+    import sys
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        if "/root/reference" in (getattr(sys.modules[k], "__file__", "") or ""):
+            del sys.modules[k]
+    saved = list(sys.path)
+    sys.path[:] = [p for p in sys.path if "/root/reference" not in p]
+    try:
+        import gnomix_b200 as g
+        assert importlib.import_module("src.model").Gnomix is g.Gnomix
+        assert importlib.import_module("src.Base.models").LogisticRegressionBase is g.LogisticRegressionBase
+        assert importlib.import_module("src.Base.models").CovRSKBase is g.CovRSKBase
+        assert importlib.import_module("src.Smooth.models").XGB_Smoother is g.XGB_Smoother
+        assert importlib.import_module("src.Smooth.models").CRF_Smoother is g.CRF_Smoother
+        sw = importlib.import_module("src.Smooth.utils").slide_window
+        from oracle import np_oracle as npo
+        B = np.random.default_rng(0).dirichlet(np.ones(3), (2, 20))
+        assert np.array_equal(sw(B, 5)[0], npo.slide_window(B, 5))
+        assert callable(importlib.import_module("src.utils").vcf_to_npy) and callable(importlib.import_module("src.postprocess").write_msp)
+        assert callable(importlib.import_module("src.Gnofix.gnofix").gnofix)
+    finally:
+        sys.path[:] = saved
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
