@@ -62,7 +62,7 @@ gbt_smooth_kernel(GbtDev m, size_t forest_bytes, const float* __restrict__ B, in
 template <int AT, bool TOPC>
 __global__ void __launch_bounds__(RK_THREADS, 1)
 gbt_smooth_rank_kernel(const __grid_constant__ GbtTopC topc, GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes,
-                       const float* __restrict__ B, int64_t N, int W, int G,
+                       const float* __restrict__ B, int64_t N, int W, int G, int Lseg,
                        float* __restrict__ proba, int32_t* __restrict__ label) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int A = AT ? AT : m.A;
@@ -77,58 +77,67 @@ gbt_smooth_rank_kernel(const __grid_constant__ GbtTopC topc, GbtDev m, const uns
     const uint4* top_s = reinterpret_cast<const uint4*>(smem + (size_t)m.T * (RK_LOWER + RK_LEAVES) * 4);
     uint32_t* rk = reinterpret_cast<uint32_t*>(smem + forest_bytes);
     const int pad = (m.S + 1) / 2;
-    const int Wp = W + 2 * pad;
     const int ast = m.astride;
-    const int hap_words = Wp * ast;
-    int* nan_flag = reinterpret_cast<int*>(rk + (size_t)G * hap_words);
+    // A unit is (haplotype, segment of Lseg windows); it needs the padded slots [w0, w0 + Lseg + S - 1).
+    // Whole chromosomes that fit shared memory are one segment (nseg == 1).
+    const int nseg = (W + Lseg - 1) / Lseg;
+    const int Lslots = Lseg + m.S - 1;
+    const int unit_words = Lslots * ast;
+    const int64_t units = N * nseg;
+    int* nan_flag = reinterpret_cast<int*>(rk + (size_t)G * unit_words);
     const int rounds = m.T / A;
 
-    for (int64_t g0 = (int64_t)blockIdx.x * G; g0 < N; g0 += (int64_t)gridDim.x * G) {
-        const int gn = (int)min((int64_t)G, N - g0);
+    for (int64_t g0 = (int64_t)blockIdx.x * G; g0 < units; g0 += (int64_t)gridDim.x * G) {
+        const int gn = (int)min((int64_t)G, units - g0);
         __syncthreads();
         if (threadIdx.x == 0) *nan_flag = 0;
         __syncthreads();
         bool saw_nan = false;
-        for (int idx = threadIdx.x; idx < gn * Wp * A; idx += blockDim.x) {
-            const int h = idx / (Wp * A), rem = idx - h * (Wp * A);
-            const int j = rem / A, a = rem - j * A;
-            const float x = __ldg(B + ((g0 + h) * W + spad_to_orig(j, W, pad)) * A + a);
+        for (int idx = threadIdx.x; idx < gn * Lslots * A; idx += blockDim.x) {
+            const int h = idx / (Lslots * A), rem = idx - h * (Lslots * A);
+            const int jl = rem / A, a = rem - jl * A;
+            const int64_t u = g0 + h, n = u / nseg;
+            const int j = (int)(u - n * nseg) * Lseg + jl;
+            float x = 0.f;
+            if (j < W + m.S - 1) x = __ldg(B + (n * W + spad_to_orig(j, W, pad)) * A + a);
             saw_nan |= (x != x);
-            rk[h * hap_words + j * ast + a] = gbt_rank_of(m.thr_table, m.K, x) << 16;
+            rk[h * unit_words + jl * ast + a] = gbt_rank_of(m.thr_table, m.K, x) << 16;
         }
         if (saw_nan) *nan_flag = 1;
         __syncthreads();
-        if (*nan_flag) {
+        const bool slow = (*nan_flag != 0);
+        if (slow) {
             // NaN inputs follow each node's default child: generic traversal on float rows
             __syncthreads();
             float* bp = reinterpret_cast<float*>(rk);
-            for (int idx = threadIdx.x; idx < gn * Wp * A; idx += blockDim.x) {
-                const int h = idx / (Wp * A), rem = idx - h * (Wp * A);
-                const int j = rem / A, a = rem - j * A;
-                bp[h * hap_words + j * A + a] = __ldg(B + ((g0 + h) * W + spad_to_orig(j, W, pad)) * A + a);
+            for (int idx = threadIdx.x; idx < gn * Lslots * A; idx += blockDim.x) {
+                const int h = idx / (Lslots * A), rem = idx - h * (Lslots * A);
+                const int jl = rem / A, a = rem - jl * A;
+                const int64_t u = g0 + h, n = u / nseg;
+                const int j = (int)(u - n * nseg) * Lseg + jl;
+                float x = 0.f;
+                if (j < W + m.S - 1) x = __ldg(B + (n * W + spad_to_orig(j, W, pad)) * A + a);
+                bp[h * unit_words + jl * A + a] = x;
             }
             __syncthreads();
-            for (int r = threadIdx.x; r < gn * W; r += blockDim.x) {
-                const int h = r / W, w = r - h * W;
-                const int64_t n = g0 + h;
-                float psum[AMAX];
-                gbt_eval_row<AT>(m, m.nodes, m.leaves, bp + h * hap_words + w * A, psum);
-                gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
-            }
-            continue;
         }
-        for (int r = threadIdx.x; r < gn * W; r += blockDim.x) {
-            const int h = r / W, w = r - h * W;
-            const int64_t n = g0 + h;
-            const unsigned char* row = reinterpret_cast<const unsigned char*>(rk + h * hap_words + w * ast);
+        for (int r = threadIdx.x; r < gn * Lseg; r += blockDim.x) {
+            const int h = r / Lseg, wl = r - h * Lseg;
+            const int64_t u = g0 + h, n = u / nseg;
+            const int w = (int)(u - n * nseg) * Lseg + wl;
+            if (w >= W) continue;
             float psum[AMAX];
-            if (TOPC) gbt_rank_walk_c<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
-            else gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
+            if (slow) {
+                gbt_eval_row<AT>(m, m.nodes, m.leaves, reinterpret_cast<const float*>(rk) + h * unit_words + wl * A, psum);
+            } else {
+                const unsigned char* row = reinterpret_cast<const unsigned char*>(rk + h * unit_words + wl * ast);
+                if (TOPC) gbt_rank_walk_c<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
+                else gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
+            }
             gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
         }
     }
 }
-
 
 // smoother.model.predict_proba(rows[k, F]) -- rows straight from global memory
 template <int AT>
@@ -318,32 +327,41 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bp_bytes = (size_t)(W + 2 * pad) * m->d.A * sizeof(float);
     const size_t smem_max = 227 * 1024;
-    GNX_REQUIRE(bp_bytes <= smem_max, "gnx_gbt_smooth: W=%d too large for shared memory", W);
     if (m->d.rank_ok && m->use_rank) {
-        // fast path: groups of G haplotypes per CTA pass, G chosen for the best row/thread fit
-        const size_t hap_bytes = (size_t)(W + 2 * pad) * m->d.astride * 4;
-        int bestG = 0;
+        // fast path: units of (haplotype, segment of Lseg windows), G units per CTA pass.  One segment
+        // per haplotype when the chromosome fits shared memory; (G, Lseg) chosen for the best fit of
+        // rows to the 1024 threads.
+        const size_t slot_bytes = (size_t)m->d.astride * 4;
+        const size_t room = smem_max - m->rank_forest_bytes - 16;
+        int bestG = 0, bestL = 0;
         double best_eff = 0.0;
-        for (int G = 1; G <= 8; G++) {
-            if (m->rank_forest_bytes + (size_t)G * hap_bytes + 16 > smem_max) break;
-            const int64_t rows = (int64_t)G * W;
-            const double eff = (double)rows / (double)(ceil_div(rows, RK_THREADS) * RK_THREADS);
-            if (eff > best_eff + 0.02) { best_eff = eff; bestG = G; }
+        for (int nseg = 1; nseg <= 64 && bestG == 0; nseg++) {
+            const int L = (int)ceil_div(W, nseg);
+            const size_t unit_bytes = (size_t)(L + m->d.S - 1) * slot_bytes;
+            if (unit_bytes > room) continue;
+            for (int G = 1; G <= 8; G++) {
+                if ((size_t)G * unit_bytes > room) break;
+                const int64_t rows = (int64_t)G * L;
+                // useful rows per pass over the thread block, discounted by the halo that is re-ranked per segment
+                const double eff = (double)rows / (double)(ceil_div(rows, RK_THREADS) * RK_THREADS) * (double)L / (double)(L + m->d.S - 1);
+                if (eff > best_eff + 0.02) { best_eff = eff; bestG = G; bestL = L; }
+            }
         }
         if (bestG > 0) {
-            const size_t smem = m->rank_forest_bytes + (size_t)bestG * hap_bytes + 16;
-            const int grid = (int)std::min<int64_t>(ceil_div(N, bestG), (int64_t)sm_count());
+            const size_t smem = m->rank_forest_bytes + (size_t)bestG * (bestL + m->d.S - 1) * slot_bytes + 16;
+            const int64_t units = N * ceil_div(W, bestL);
+            const int grid = (int)std::min<int64_t>(ceil_div(units, bestG), (int64_t)sm_count());
 #define CALLR(AT)                                                                                                              \
     do {                                                                                                                       \
         if (m->h_topc) {                                                                                                       \
             GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             gbt_smooth_rank_kernel<AT, true><<<grid, RK_THREADS, smem, st>>>(*m->h_topc, m->d, m->rank_forest, m->rank_forest_bytes, \
-                                                                             B_dev, N, W, bestG, proba_dev, label_dev);        \
+                                                                             B_dev, N, W, bestG, bestL, proba_dev, label_dev); \
         } else {                                                                                                               \
             static const GbtTopC none{};                                                                                       \
             GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             gbt_smooth_rank_kernel<AT, false><<<grid, RK_THREADS, smem, st>>>(none, m->d, m->rank_forest, m->rank_forest_bytes, \
-                                                                              B_dev, N, W, bestG, proba_dev, label_dev);       \
+                                                                              B_dev, N, W, bestG, bestL, proba_dev, label_dev); \
         }                                                                                                                      \
     } while (0)
             GBT_DISPATCH_A(m->d.A, CALLR)
@@ -352,6 +370,7 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
             return 0;
         }
     }
+    GNX_REQUIRE(bp_bytes <= smem_max, "gnx_gbt_smooth: W=%d too large for the generic kernel's shared-memory row (forests deeper than 4 levels)", W);
     const bool forest_smem = m->forest_bytes + bp_bytes <= smem_max;
     const size_t smem = bp_bytes + (forest_smem ? m->forest_bytes : 0);
     const int grid = (int)std::min<int64_t>(N, (int64_t)sm_count() * (forest_smem ? 1 : 2));

@@ -43,6 +43,22 @@ def test_gbt_smooth_matches_oracle(W, A, S, N, depth, kernel):
     assert np.array_equal(label, np.argmax(np.nan_to_num(proba, nan=-1.0), axis=-1))
 
 
+def test_gbt_many_windows_are_segmented():
+    """W far beyond what one shared-memory row holds (fine window sizes, e.g. 0.05 cM on chr1):
+    the rank-form kernel walks the haplotype in segments with an S-1 halo; same bits."""
+    from gnomix_b200 import GBTForest
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(77)
+    W, A, S, N = 9001, 7, 75, 3
+    forest = GBTForest.random(rng, A, S, n_rounds=10, depth=4)
+    B = util.smooth_B(rng, N, W, A)
+    B[1, 4000, 2] = np.nan
+    sm = _smoother(W, A, S, forest)
+    proba, label = sm.predict_proba(B), sm.predict(B)
+    p_o, l_o = co.gbt_smooth(forest, B, S)
+    assert np.array_equal(proba.view(np.uint32), p_o.view(np.uint32)) and np.array_equal(label, l_o)
+
+
 def test_gbt_thresholds_hit_exactly():
     """Inputs equal to split thresholds (and one ulp either side) take the same branch as the
     float compare: the rank transform is exact."""
