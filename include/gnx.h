@@ -56,7 +56,10 @@ int gnx_selftest_math(int64_t n, uint64_t seed, int64_t* mismatches);
  *            reference's padded window (reflect pad included), A_rows = A (A > 2)
  *            or 1 (A == 2, sklearn binary layout).
  * intercept: [W, A_rows] float64.
- * limbs:     signed base-256 digits per fixed-point weight (0 = default 7).
+ * limbs:     signed base-256 digits per fixed-point weight (0 = default 7; A > 8 uses
+ *            16-column limb groups and at most 4 limbs).  Windows up to 32000 SNPs.
+ * Environment GNX_LR_DBG (bit mask, profiling only): 1 skip MMAs, 2 skip the
+ * epilogue, 4 skip weight loads -- results are garbage when set.
  * W is implied: W = C / M.  Output B float32 (or float64) [N, W, A].
  * ------------------------------------------------------------------------- */
 int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx,
@@ -139,9 +142,12 @@ int gnx_svc_kernel_window(const gnx_svc_t* m, int w, const int8_t* X_dev, int64_
  * K6  Gnomix.phase / gnofix with the reference's default arguments
  * replaces: src/model.py:188-214 and src/Gnofix/gnofix.py:58-208 (+ phasing.py:
  *           182-198) for all individuals in one launch.
- * X_dev [2n, ldX] int8 and B_dev [2n, W, A] float32 are updated IN PLACE (tails
- * swapped); Y_dev [2n, W] int32 receives the final labels; tracker_dev [2n, W]
- * int32 (nullable) the gnofix_tracker rows.
+ * X_dev [2n, ldX] int8 (nullable: skips the SNP-level swap) and B_dev [2n, W, A]
+ * float32 are updated IN PLACE (tails swapped); Y_dev [2n, W] int32 receives the
+ * final labels; tracker_dev [2n, W] int32 (nullable) the gnofix_tracker rows.
+ * Needs W >= 2*S (as XGB_Smoother asserts), max_it <= 64, a forest of depth <= 4
+ * with <= 65535 distinct thresholds, and finite B (NaN ranks above every threshold
+ * instead of following default children).
  * ------------------------------------------------------------------------- */
 int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float* B_dev,
                int64_t n_ind, int W, int max_it, int32_t* Y_dev, int32_t* tracker_dev,
