@@ -103,18 +103,20 @@ class Base:
     def predict_proba(self, X):
         """X [N, C] int8 (numpy, or a torch cuda tensor for HBM-resident pipelines)
         -> B [N, W, A]: numpy float64 for numpy input (the reference's dtype), a torch
-        cuda float32 tensor for cuda input."""
+        cuda float32 tensor for cuda input (float32 is what every smoother consumes)."""
         _lib.require_gpu()
         import torch
         t = time()
         Xd, ld = to_device_haplotypes(X)
         assert Xd.shape[1] == self.C, "expected %d SNPs, got %d" % (self.C, Xd.shape[1])
-        Bd = self._device_predict(Xd, ld)
         if _is_torch(X) and X.is_cuda:
-            out = Bd
+            out = self._device_predict(Xd, ld)
         else:
+            # host callers get what the reference returns: float64 (the float64 epilogue's own values,
+            # not float32 widened); rounding them to float32 gives exactly the device-resident result
+            Bd = self._device_predict(Xd, ld, dtype=torch.float64)
             torch.cuda.current_stream().synchronize()
-            out = Bd.cpu().numpy().astype(np.float64)
+            out = Bd.cpu().numpy()
         self.time["inference"] = time() - t
         return out
 
