@@ -124,7 +124,7 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
     GNX_REQUIRE(L >= 2, "gnx_lr_model_create: limbs=%d too small", L);
     const int64_t W = C / M, rem = C - M * W, M_ = M + 2 * ctx;
     GNX_REQUIRE(W < (1 << 30), "too many windows");
-    GNX_REQUIRE(M_ + rem <= 32000, "gnx_lr_model_create: windows of %lld SNPs exceed the 32000 the int32 limb accumulators allow", (long long)(M_ + rem));
+    GNX_REQUIRE(M_ + rem <= 131000, "gnx_lr_model_create: windows of %lld SNPs exceed the 131000 the int32 limb accumulators allow", (long long)(M_ + rem));
 
     // padded window ranges, folded original ranges
     std::vector<int64_t> lo(W), len(W), s0(W), e0(W), coff(W);

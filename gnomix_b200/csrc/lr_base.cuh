@@ -65,16 +65,13 @@ __device__ __forceinline__ void lr_epilogue_store(const int32_t (&acc)[LR_NCOLS]
     const double scale = gnx_pow2i(-m.s);
 #pragma unroll
     for (int a = 0; a < APAD; a++) {
-        // limbs pairwise in int32 first (|acc| < 2^23 for windows <= 32768 SNPs, checked at model
-        // create), then three exact 64-bit steps: tot = sum_l acc_l * 256^l
+        // exact 64-bit Horner over the limbs: tot = sum_l acc_l * 256^l.  No overflow: the scale is
+        // chosen at model create so that 2 * sum |q| < 2^62 (|x| <= 2), and the int32 accumulators
+        // hold for windows up to 131000 SNPs
         long long tot = 0;
 #pragma unroll
-        for (int j = LMAX / 2 - 1 + (LMAX & 1); j >= 0; j--) {
-            int pr = 0;
-            if (2 * j + 1 < LMAX && 2 * j + 1 < m.L) pr = acc[(2 * j + 1) * APAD + a] * 256;
-            if (2 * j < m.L) pr += acc[(2 * j) * APAD + a];
-            tot = tot * 65536 + (long long)pr;
-        }
+        for (int l = LMAX - 1; l >= 0; l--)
+            if (l < m.L) tot = tot * 256 + (long long)acc[l * APAD + a];
         d[a] = 0.0;
         if (a < m.Ar) d[a] = GNX_ADD(GNX_MUL(GNX_LL2D(tot), scale), __ldg(m.bias + (int64_t)w * m.Ar + a));
     }

@@ -57,7 +57,9 @@ int gnx_selftest_math(int64_t n, uint64_t seed, int64_t* mismatches);
  *            or 1 (A == 2, sklearn binary layout).
  * intercept: [W, A_rows] float64.
  * limbs:     signed base-256 digits per fixed-point weight (0 = default 7; A > 8 uses
- *            16-column limb groups and at most 4 limbs).  Windows up to 32000 SNPs.
+ *            16-column limb groups and at most 4 limbs).  Windows up to 131000 SNPs.  The
+ *            fixed-point scale is chosen so that the int64 totals cannot overflow for
+ *            |x| <= 2 (the reference's matrix only holds {0,1,2}).
  * Environment GNX_LR_DBG (bit mask, profiling only): 1 skip MMAs, 2 skip the
  * epilogue, 4 skip weight loads -- results are garbage when set.
  * W is implied: W = C / M.  Output B float32 (or float64) [N, W, A].
