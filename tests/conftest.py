@@ -18,7 +18,19 @@ def pytest_collection_modifyitems(config, items):
     pass
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the CUDA library (nvcc cross-compiles without a GPU) and the C oracle once per session when
+    they are missing or stale; the built files are git-ignored."""
+    import shutil
+    from gnomix_b200 import build as b
+    if b.is_stale() and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        b.build_lib()
+    from oracle import c_oracle
+    c_oracle.build()
+
+
 @pytest.fixture(scope="session")
-def libgnx():
+def libgnx(_built):
     from gnomix_b200 import _lib
     return _lib.lib()
