@@ -239,3 +239,36 @@ def test_reference_import_paths_resolve_to_this_package():
         sys.path[:] = saved
         for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
             del sys.modules[k]
+
+
+def test_xgboost_json_roundtrip_and_exported_model(tmp_path):
+    """convert.py: a forest written in xgboost's JSON model schema parses back to the same arrays, and an
+    exported-model .npz (the format scripts/export_reference_model.py writes) loads into a Gnomix."""
+    import json
+    from gnomix_b200 import GBTForest
+    from gnomix_b200.convert import forest_from_xgboost_json, forest_to_xgboost_json, load_exported_model
+    from tests import util
+    rng = np.random.default_rng(3)
+    A, S = 3, 5
+    f = GBTForest.random(rng, A, S, n_rounds=4, depth=3)
+    # make it ragged: turn one internal node of tree 0 into a leaf by rewriting the arrays through JSON
+    js = forest_to_xgboost_json(f)
+    txt = json.dumps(js)
+    g = forest_from_xgboost_json(txt)
+    for name in ("feat", "thr", "left", "right", "default_left", "leaf", "tree_offsets", "base_margin"):
+        assert np.array_equal(getattr(f, name), getattr(g, name)), name
+    p = tmp_path / "m.json"
+    p.write_text(txt)
+    assert forest_from_xgboost_json(str(p)).n_trees == f.n_trees
+    # exported model file
+    C, M = 3000, 250
+    coefs, icpts, ctx = util.random_lr(rng, C, M, A)
+    np.savez_compressed(tmp_path / "exp.npz", C=C, M=M, A=A, S=S, context=ctx, context_ratio=0.5, snp_pos=np.arange(C) * 10 + 5,
+                        snp_ref=np.array(["A"] * C), snp_alt=np.array(["G"] * C), population_order=np.array(["X", "Y", "Z"]),
+                        lr_coef=np.concatenate([c.ravel() for c in coefs]), lr_intercept=np.stack(icpts), xgb_json=np.array(txt),
+                        gen_map_chm=np.array(["22", "22"]), gen_map_pos=np.array([1, 40000]), gen_map_cm=np.array([0.0, 1.5]))
+    m = load_exported_model(str(tmp_path / "exp.npz"))
+    assert m.W == C // M and m.population_order == ["X", "Y", "Z"] and m.smooth.model.n_trees == f.n_trees
+    c2, b2 = m.base.packed_weights()
+    assert np.array_equal(c2, np.concatenate([c.ravel() for c in coefs])) and np.array_equal(b2, np.stack(icpts))
+    assert list(m.gen_map_df["pos"]) == [1, 40000]
