@@ -12,7 +12,9 @@ already resident in HBM as int8.  Workload = BASELINE.json configs[2]: chr1 geom
 smoother, 50,000 haplotypes PER GPU (weak scaling: every rank owns its own shard, no
 collective on the data path).  `value` = haplotypes of all ranks / max-over-ranks step
 time; `e2e` = the same metric through the host-buffer C-ABI entry point gnx_infer_host
-(pinned host int8 in, labels out, H2D/D2H inside the timed region).
+(pinned host int8 in, labels out, H2D/D2H inside the timed region; by default the host
+cores pack part of every chunk to 2 bits per SNP while the DMA engine moves the rest raw --
+`e2e.unpacked` is the same call with packing off).
 
 Prints ONE JSON line on rank 0.
 """
@@ -261,21 +263,35 @@ def run_ours(args):
     Lh = torch.empty((n_e2e, W), dtype=torch.int32, pin_memory=True)
     torch.cuda.synchronize()
 
+    import ctypes as C_
+
     def e2e_step():
         _lib.check(lib.gnx_infer_host(hlr, hgbt, Xh.data_ptr(), n_e2e, ld, None, Lh.data_ptr(), 0), "gnx_infer_host")
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    def e2e_measure():
         e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n_e2e * world / float(te.item())
-    labels_match = bool(torch.equal(Lh.cuda(), L[:n_e2e]))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        frac, h2d, d2h = C_.c_double(0), C_.c_int64(0), C_.c_int64(0)
+        lib.gnx_infer_host_last_transfer(C_.byref(frac), C_.byref(h2d), C_.byref(d2h))
+        return n_e2e * world / float(te.item()), frac.value, h2d.value, d2h.value, bool(torch.equal(Lh.cuda(), L[:n_e2e]))
+
+    # default path: part of every chunk crosses PCIe as 2-bit planes packed by the host cores
+    e2e_value, e2e_frac, e2e_h2d, e2e_d2h, labels_match = e2e_measure()
+    pk, h2dr = C_.c_double(0), C_.c_double(0)
+    lib.gnx_infer_host_rates(C_.byref(pk), C_.byref(h2dr))
+    # for comparison: the same call with packing switched off (raw int8 over PCIe)
+    os.environ["GNX_HOST_PACK"] = "0"
+    raw_value, _, raw_h2d, _, raw_match = e2e_measure()
+    del os.environ["GNX_HOST_PACK"]
+    labels_match = labels_match and raw_match
 
     if rank != 0:
         if world > 1:
@@ -322,9 +338,12 @@ def run_ours(args):
                                % (C, M, W, A, S, N),
                    "forest": forest_kind, "l2": "inputs (%.1f GB/GPU) exceed L2, no flush needed" % (N * ld / 1e9),
                    "parallelism": "haplotype shards, one rank per GPU, no collective on the data path"},
-        "e2e": {"value": e2e_value, "unit": "haplotypes/s", "h2d_bytes_per_step": int(n_e2e * C),
-                "d2h_bytes_per_step": int(n_e2e * W * 4), "haplotypes_per_step": n_e2e,
-                "api": "gnx_infer_host (pinned host int8 in, int32 labels out)", "labels_match_resident_path": labels_match},
+        "e2e": {"value": e2e_value, "unit": "haplotypes/s", "h2d_bytes_per_step": int(e2e_h2d),
+                "d2h_bytes_per_step": int(e2e_d2h), "haplotypes_per_step": n_e2e,
+                "api": "gnx_infer_host (pinned host int8 in, int32 labels out)", "labels_match_resident_path": labels_match,
+                "packed_fraction_of_rows": e2e_frac, "host_threads": int(lib.gnx_host_threads()),
+                "calibrated_host_pack_gbs": pk.value, "calibrated_h2d_gbs": h2dr.value,
+                "unpacked": {"value": raw_value, "h2d_bytes_per_step": int(raw_h2d)}},
         "gpu_launches": 2 * args.steps,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": kernels[dom]["frac_hbm"], "traffic": traffic.get(dom), "peak_source": peak_src,

@@ -43,6 +43,11 @@ _SIGS = {
     "gnx_svc_kernel_window": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "gnx_gnofix": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "gnx_infer_host": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64]),
+    "gnx_pack_rows_host": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, C.c_int, C.POINTER(C.c_int)]),
+    "gnx_unpack_dev": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "gnx_host_threads": (C.c_int, []),
+    "gnx_infer_host_rates": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "gnx_infer_host_last_transfer": (C.c_int, [C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(c_i64)]),
 }
 
 EXPORTS = tuple(_SIGS)

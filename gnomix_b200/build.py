@@ -22,12 +22,13 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def _deps():
     inc = os.path.join(HERE, "..", "include")
-    return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(inc, "*.h"))
+    return (sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))
+            + glob.glob(os.path.join(inc, "*.h")))
 
 
 def is_stale() -> bool:
@@ -51,9 +52,9 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in sources():
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(objdir, os.path.splitext(os.path.basename(src))[0] + ".o")
         objs.append(obj)
-        if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(p) for p in _deps() if not p.endswith(".cu") or p == src):
+        if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(p) for p in _deps() if not p.endswith((".cu", ".cpp")) or p == src):
             continue
         cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", src, "-o", obj]
         if verbose:
@@ -66,7 +67,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         if verbose and out:
             print(out)
     tmp = LIB + ".tmp"
-    cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
+    cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-lpthread"]
     subprocess.check_call(cmd, env=env)
     os.replace(tmp, LIB)
     return LIB

@@ -1,0 +1,18 @@
+// host_pack.h -- 2-bit-plane packing of the int8 haplotype matrix on the host cores
+// (host_pack.cpp) and its device-side inverse (pack.cu); used by gnx_infer_host.
+#pragma once
+
+#include <stdint.h>
+
+namespace gnx {
+
+// Packs rows [0, n) of X (int8 [n, ldX], C valid columns) into out (row pitch
+// out_pitch_words 64-bit words, >= 2 * ceil(C / 64)) with `threads` host threads
+// (<= 0: all cores this process may run on, or GNX_HOST_THREADS).  Returns 1 if any
+// value was outside 0..3 (the packed form is then lossy and must not be used).
+// *isa receives 0 scalar / 1 AVX2 / 2 AVX-512BW.
+int pack_rows(const int8_t* X, int64_t n, int64_t ldX, int64_t C, uint64_t* out, int64_t out_pitch_words, int threads,
+              int* isa);
+int host_threads_default();
+
+}  // namespace gnx

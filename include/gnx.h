@@ -158,12 +158,41 @@ int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float*
 /* ---------------------------------------------------------------------------
  * Host-buffer pipeline: Gnomix.predict_proba / predict on a numpy-style host
  * matrix (src/model.py:169-179, gnomix.py:55-58).  Streams haplotype chunks
- * through pinned staging buffers (H2D, K1, K4, D2H overlapped on two streams).
+ * through two device slots (H2D, K1, K4, D2H overlapped on two streams); part of
+ * every chunk crosses PCIe as 2-bit planes packed by the host cores (see below).
  * X_host may be pageable or pinned.  proba_host [N,W,A] float32 may be NULL.
  * Synchronous: returns when label_host / proba_host are complete.
+ * Environment: GNX_HOST_PACK=0 (no packing), GNX_HOST_PACK_FRAC=f (packed fraction of
+ * each chunk instead of the calibrated one), GNX_HOST_THREADS=n.
  * ------------------------------------------------------------------------- */
 int gnx_infer_host(const gnx_lr_t* lr, const gnx_gbt_t* gbt, const int8_t* X_host, int64_t N,
                    int64_t ldX, float* proba_host, int32_t* label_host, int64_t chunk_haps);
+
+/* ---------------------------------------------------------------------------
+ * Packed transfer of the haplotype matrix (the reference's int8 matrix,
+ * src/utils.py:104-159, carries 2 bits per byte): gnx_infer_host packs on the host
+ * cores while the previous chunk is in flight and unpacks on the device, so a quarter
+ * of the bytes cross PCIe (GNX_HOST_PACK=0 disables it).  The two halves are exported
+ * for callers that stage their own transfers.
+ * Packed row: group g (SNPs 64g..64g+63) = { u64 plane0, u64 plane1 }, bit i of
+ * planeK = bit K of X[row][64g+i]; pitch_words >= 2*ceil(C/64) 64-bit words per row.
+ * gnx_pack_rows_host: pure host code (no device needed); *out_of_range = 1 if some
+ * value was outside 0..3 (packed form unusable).  threads <= 0: gnx_host_threads().
+ * gnx_unpack_dev: X_dev [n, ldX] int8, ldX % 16 == 0, columns [0, min(ldX, 32*pitch_words))
+ * are written (SNPs >= C as 0).
+ * ------------------------------------------------------------------------- */
+int gnx_pack_rows_host(const int8_t* X_host, int64_t n, int64_t ldX, int64_t C, uint64_t* packed_host,
+                       int64_t pitch_words, int threads, int* out_of_range);
+int gnx_unpack_dev(const uint64_t* packed_dev, int64_t n, int64_t pitch_words, int64_t C,
+                   int8_t* X_dev, int64_t ldX, void* stream);
+/* rates measured by gnx_infer_host's one-off calibration (0 before it ran): host pack
+ * rate in GB/s of int8 input, pinned H2D rate in GB/s */
+int gnx_infer_host_rates(double* pack_gbs, double* h2d_gbs);
+/* what the last gnx_infer_host call moved: packed fraction of each chunk's rows, bytes
+ * copied host->device and device->host */
+int gnx_infer_host_last_transfer(double* frac, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* host threads the library uses (cores this process may run on, or GNX_HOST_THREADS) */
+int gnx_host_threads(void);
 
 #ifdef __cplusplus
 }

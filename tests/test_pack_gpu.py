@@ -1,0 +1,80 @@
+"""Packed H2D path on the device: unpack(pack(X)) == X, and gnx_infer_host gives the same labels and
+probabilities whatever share of each chunk crosses the bus packed (including chunks that cannot be
+packed because they hold values outside 0..3)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def test_unpack_inverts_pack(libgnx):
+    import torch
+    from gnomix_b200 import _lib
+    _lib.require_gpu()
+    rng = np.random.default_rng(8)
+    for n, cols in [(1, 1), (3, 64), (7, 129), (33, 60037), (300, 317_408)]:
+        ld = (cols + 127) // 128 * 128
+        X = rng.integers(0, 4, size=(n, ld), dtype=np.int8)
+        X[:, cols:] = 0
+        pw = ld // 32
+        packed = np.empty((n, pw), dtype=np.uint64)
+        bad = C.c_int(0)
+        assert libgnx.gnx_pack_rows_host(X.ctypes.data, n, ld, cols, packed.ctypes.data, pw, 0, C.byref(bad)) == 0 and bad.value == 0
+        pd = torch.from_numpy(packed.view(np.int64)).cuda()
+        Xd = torch.full((n, ld), 9, dtype=torch.int8, device="cuda")
+        _lib.check(libgnx.gnx_unpack_dev(pd.data_ptr(), n, pw, cols, Xd.data_ptr(), ld, None), "gnx_unpack_dev")
+        torch.cuda.synchronize()
+        assert np.array_equal(Xd.cpu().numpy(), X), (n, cols)
+
+
+def _model(C_, M, A, S, seed):
+    from gnomix_b200 import Gnomix, GBTForest
+    rng = np.random.default_rng(seed)
+    model = Gnomix(C_, M, A, S)
+    coefs, icpts, _ = util.random_lr(rng, C_, M, A)
+    model.base.set_window_weights(coefs, icpts)
+    model.smooth.model = GBTForest.random(rng, A, model.smooth.S, n_rounds=20, depth=4)
+    return model, rng
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_infer_host_same_results_for_every_packed_fraction(pinned, monkeypatch):
+    import torch
+    C_, M, A, S, N = 40_013, 500, 7, 15, 1100
+    model, rng = _model(C_, M, A, S, 21)
+    X = util.random_haplotypes(rng, N, C_)
+    Xh = torch.from_numpy(X).pin_memory() if pinned else X
+    monkeypatch.setenv("GNX_HOST_PACK", "0")
+    ref_l, ref_p = model.predict_host(Xh, want_proba=True, chunk_haps=256)
+    # resident path
+    B = model.base.predict_proba(torch.from_numpy(X).cuda())
+    P, L = model.smooth._device_smooth(B)
+    assert np.array_equal(ref_l, L.cpu().numpy()) and np.array_equal(ref_p, P.cpu().numpy())
+    monkeypatch.delenv("GNX_HOST_PACK")
+    for frac in [None, "0", "0.37", "1"]:
+        if frac is None:
+            monkeypatch.delenv("GNX_HOST_PACK_FRAC", raising=False)
+        else:
+            monkeypatch.setenv("GNX_HOST_PACK_FRAC", frac)
+        for chunk in (256, 0):
+            l, p = model.predict_host(Xh, want_proba=True, chunk_haps=chunk)
+            assert np.array_equal(l, ref_l) and np.array_equal(p, ref_p), (frac, chunk)
+    monkeypatch.delenv("GNX_HOST_PACK_FRAC", raising=False)
+    # a chunk with an unpackable value goes raw; results still equal the unpacked path on the same input
+    X2 = X.copy()
+    X2[300, 17] = 5
+    X2[900, C_ - 1] = -3
+    X2h = torch.from_numpy(X2).pin_memory() if pinned else X2
+    monkeypatch.setenv("GNX_HOST_PACK", "0")
+    r2 = model.predict_host(X2h, chunk_haps=256)
+    monkeypatch.delenv("GNX_HOST_PACK")
+    assert np.array_equal(model.predict_host(X2h, chunk_haps=256), r2)
+    if pinned:
+        pk, h2d = C.c_double(0), C.c_double(0)
+        from gnomix_b200 import _lib
+        _lib.lib().gnx_infer_host_rates(C.byref(pk), C.byref(h2d))
+        assert pk.value > 0 and h2d.value > 0
