@@ -7,6 +7,7 @@
 // probabilities of haplotype n, which one CTA keeps in shared memory next to the
 // whole forest.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -59,9 +60,9 @@ gbt_smooth_kernel(GbtDev m, size_t forest_bytes, const float* __restrict__ B, in
 // is: node word -> (byte offset of the feature in the row, threshold index) -> one
 // integer compare against the pre-ranked input.  Rank rows hold rank << 16, node words
 // are (k << 16 | byte offset), so `x < thr`  <=>  !(rank_word > node_word).
-template <int AT, bool TOPC>
+template <int AT, int VAR, typename TOPT>
 __global__ void __launch_bounds__(RK_THREADS, 1)
-gbt_smooth_rank_kernel(const __grid_constant__ GbtTopC topc, GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes,
+gbt_smooth_rank_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes,
                        const float* __restrict__ B, int64_t N, int W, int G, int Lseg,
                        float* __restrict__ proba, int32_t* __restrict__ label) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -72,9 +73,12 @@ gbt_smooth_rank_kernel(const __grid_constant__ GbtTopC topc, GbtDev m, const uns
         uint4* dst = reinterpret_cast<uint4*>(smem);
         for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
+    // VAR 2 (wide): lower uint2 [T][12] | leaves [T][16];  VAR 0/1: lower u32 [T][12] | leaves | top uint4 [T]
+    constexpr int NODE_B = (VAR == 2) ? 8 : 4;
     const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
-    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * RK_LOWER * 4);
+    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * RK_LOWER * NODE_B);
     const uint4* top_s = reinterpret_cast<const uint4*>(smem + (size_t)m.T * (RK_LOWER + RK_LEAVES) * 4);
+    (void)top_s;
     uint32_t* rk = reinterpret_cast<uint32_t*>(smem + forest_bytes);
     const int pad = (m.S + 1) / 2;
     const int ast = m.astride;
@@ -131,8 +135,13 @@ gbt_smooth_rank_kernel(const __grid_constant__ GbtTopC topc, GbtDev m, const uns
                 gbt_eval_row<AT>(m, m.nodes, m.leaves, reinterpret_cast<const float*>(rk) + h * unit_words + wl * A, psum);
             } else {
                 const unsigned char* row = reinterpret_cast<const unsigned char*>(rk + h * unit_words + wl * ast);
-                if (TOPC) gbt_rank_walk_c<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
-                else gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
+                if constexpr (VAR == 2)
+                    gbt_rank_walk_w<AT>(A, row, topc, reinterpret_cast<const unsigned char*>(lower_s),
+                                        reinterpret_cast<const unsigned char*>(leaves_s), rounds, psum);
+                else if constexpr (VAR == 1)
+                    gbt_rank_walk_c<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
+                else
+                    gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
             }
             gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
         }
@@ -261,14 +270,28 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
             memcpy(rleaves + (size_t)t * RK_LEAVES, leaves.data() + (size_t)t * n_leaf, sizeof(float) * RK_LEAVES);
         }
     }
+    // wide image: lower uint2 [T][12] | leaves [T][16]
+    std::vector<uint32_t> wimg;
+    if (rank_ok) {
+        wimg.assign((size_t)n_trees * (2 * RK_LOWER + RK_LEAVES), 0u);
+        const uint32_t* lower = rimg.data();
+        for (size_t i = 0; i < (size_t)n_trees * RK_LOWER; i++) {
+            wimg[2 * i] = lower[i] & 0xffff0000u;
+            wimg[2 * i + 1] = lower[i] & 0xffffu;
+        }
+        memcpy(wimg.data() + (size_t)n_trees * 2 * RK_LOWER, rimg.data() + (size_t)n_trees * RK_LOWER,
+               sizeof(uint32_t) * (size_t)n_trees * RK_LEAVES);
+    }
+    const size_t wb = (wimg.size() * 4 + 15) & ~size_t(15);
     const size_t rb = rimg.size() * 4, tb = ((size_t)K * 4 + 15) & ~size_t(15);
     char* blob = nullptr;
-    GNX_CUDA(cudaMalloc((void**)&blob, forest + 256 + rb + tb + 16));
+    GNX_CUDA(cudaMalloc((void**)&blob, forest + 256 + rb + tb + wb + 16));
     bool ok = cudaMemcpy(blob, nodes.data(), nb, cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(blob + nb, leaves.data(), lb, cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(blob + forest, base_margin, sizeof(float) * A, cudaMemcpyHostToDevice) == cudaSuccess;
     if (rb) ok &= cudaMemcpy(blob + forest + 256, rimg.data(), rb, cudaMemcpyHostToDevice) == cudaSuccess;
     if (K) ok &= cudaMemcpy(blob + forest + 256 + rb, tab.data(), (size_t)K * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (wb) ok &= cudaMemcpy(blob + forest + 256 + rb + tb, wimg.data(), wimg.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         cudaFree(blob);
         set_error("gnx_gbt_model_create: H2D copy failed");
@@ -293,6 +316,20 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
         for (int t = 0; t < n_trees; t++)
             for (int k = 0; k < 3; k++) m->h_topc->w[3 * t + k] = top[(size_t)t * 4 + k];
     }
+    m->h_topw = nullptr;
+    m->wide_forest = reinterpret_cast<const unsigned char*>(blob + forest + 256 + rb + tb);
+    m->wide_forest_bytes = wb;
+    if (rank_ok && n_trees <= GBT_TOPW_MAX_T) {
+        m->h_topw = new GbtTopW();
+        const uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
+        for (int t = 0; t < n_trees; t++)
+            for (int k = 0; k < 3; k++) m->h_topw->w[3 * t + k] = make_uint2(top[(size_t)t * 4 + k] & 0xffff0000u, top[(size_t)t * 4 + k] & 0xffffu);
+    }
+    m->variant = m->h_topw ? 2 : (m->h_topc ? 1 : 0);
+    if (const char* e = getenv("GNX_GBT_VARIANT")) {  // profiling / cross-check switch
+        const int v = atoi(e);
+        if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw)) m->variant = v;
+    }
     *out = m;
     return 0;
 }
@@ -300,6 +337,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
 void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     if (!m) return;
     if (m->d_blob) cudaFree(m->d_blob);
+    delete m->h_topw;
     delete m->h_topc;
     delete m;
 }
@@ -332,7 +370,10 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
         // per haplotype when the chromosome fits shared memory; (G, Lseg) chosen for the best fit of
         // rows to the 1024 threads.
         const size_t slot_bytes = (size_t)m->d.astride * 4;
-        const size_t room = smem_max - m->rank_forest_bytes - 16;
+        const int var = m->variant;
+        const size_t img_bytes = (var == 2) ? m->wide_forest_bytes : m->rank_forest_bytes;
+        const unsigned char* img = (var == 2) ? m->wide_forest : m->rank_forest;
+        const size_t room = smem_max - img_bytes - 16;
         int bestG = 0, bestL = 0;
         double best_eff = 0.0;
         for (int nseg = 1; nseg <= 64 && bestG == 0; nseg++) {
@@ -348,24 +389,29 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
             }
         }
         if (bestG > 0) {
-            const size_t smem = m->rank_forest_bytes + (size_t)bestG * (bestL + m->d.S - 1) * slot_bytes + 16;
+            const size_t smem = img_bytes + (size_t)bestG * (bestL + m->d.S - 1) * slot_bytes + 16;
             const int64_t units = N * ceil_div(W, bestL);
             const int grid = (int)std::min<int64_t>(ceil_div(units, bestG), (int64_t)sm_count());
-#define CALLR(AT)                                                                                                              \
+#define LAUNCHR(AT, VAR, TOPT, TOPV)                                                                                           \
     do {                                                                                                                       \
-        if (m->h_topc) {                                                                                                       \
-            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gbt_smooth_rank_kernel<AT, true><<<grid, RK_THREADS, smem, st>>>(*m->h_topc, m->d, m->rank_forest, m->rank_forest_bytes, \
-                                                                             B_dev, N, W, bestG, bestL, proba_dev, label_dev); \
-        } else {                                                                                                               \
-            static const GbtTopC none{};                                                                                       \
-            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gbt_smooth_rank_kernel<AT, false><<<grid, RK_THREADS, smem, st>>>(none, m->d, m->rank_forest, m->rank_forest_bytes, \
-                                                                              B_dev, N, W, bestG, bestL, proba_dev, label_dev); \
-        }                                                                                                                      \
+        GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_rank_kernel<AT, VAR, TOPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gbt_smooth_rank_kernel<AT, VAR, TOPT><<<grid, RK_THREADS, smem, st>>>(TOPV, m->d, img, img_bytes, B_dev, N, W, bestG, bestL, \
+                                                                              proba_dev, label_dev);                           \
+    } while (0)
+#define CALLR(AT)                                                  \
+    do {                                                           \
+        if (var == 2) {                                            \
+            LAUNCHR(AT, 2, GbtTopW, *m->h_topw);                   \
+        } else if (var == 1) {                                     \
+            LAUNCHR(AT, 1, GbtTopC, *m->h_topc);                   \
+        } else {                                                   \
+            static const GbtTopC none{};                           \
+            LAUNCHR(AT, 0, GbtTopC, none);                         \
+        }                                                          \
     } while (0)
             GBT_DISPATCH_A(m->d.A, CALLR)
 #undef CALLR
+#undef LAUNCHR
             GNX_CUDA(cudaGetLastError());
             return 0;
         }
@@ -392,7 +438,16 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
 
 int gnx_gbt_set_kernel(gnx_gbt_t* m, int which) {
     GNX_REQUIRE(m != nullptr, "gnx_gbt_set_kernel: NULL model");
-    GNX_REQUIRE(which == 0 || which == 1, "gnx_gbt_set_kernel: unknown kernel %d", which);
+    GNX_REQUIRE(which == 0 || which == 1 || (which >= 10 && which <= 12), "gnx_gbt_set_kernel: unknown kernel %d", which);
+    if (which >= 10) {  // rank-form flavour: 10 narrow nodes, 11 narrow + parameter-bank tops, 12 wide nodes
+        const int v = which - 10;
+        m->use_rank = 1;
+        if (!m->d.rank_ok) return 0;  // not a rank-form forest: the generic kernel runs whatever the flavour
+        GNX_REQUIRE(v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw), "gnx_gbt_set_kernel: flavour %d not available for this forest", v);
+        m->variant = v;
+        m->use_rank = 1;
+        return 0;
+    }
     m->use_rank = (which == 0);
     return 0;
 }

@@ -196,6 +196,49 @@ __device__ __forceinline__ void gbt_rank_walk_c(int A, const unsigned char* __re
     }
 }
 
+// Wide-node variant (default of gbt_smooth): every node is two words { k << 16, byte offset of the
+// feature in a row }, so the feature address is one add (no mask) and the walk carries BYTE offsets
+// into the level-2 / level-3 / leaf arrays (select + shift-add per level instead of index arithmetic).
+// Top three nodes of every tree in the kernel parameter bank, nodes 3..14 (uint2) and leaves in
+// shared memory: 160 B per tree.
+constexpr int GBT_TOPW_MAX_T = 1024;
+struct GbtTopW {
+    uint2 w[3 * GBT_TOPW_MAX_T];
+};
+
+template <int AT>
+__device__ __forceinline__ void gbt_rank_walk_w(int A, const unsigned char* __restrict__ row, const GbtTopW& top,
+                                                const unsigned char* __restrict__ lw, const unsigned char* __restrict__ lv,
+                                                int rounds, float* psum) {
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+    int tbase = 0;
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const uint2 t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
+                const bool b0 = *reinterpret_cast<const uint32_t*>(row + t0.y) > t0.x;
+                const uint2 n1 = b0 ? t2 : t1;
+                const bool b1 = *reinterpret_cast<const uint32_t*>(row + n1.y) > n1.x;
+                uint32_t o = (b0 ? 16u : 0u) + (b1 ? 8u : 0u);
+                const uint2 n2 = *reinterpret_cast<const uint2*>(lw + c * (RK_LOWER * 8) + o);
+                const bool b2 = *reinterpret_cast<const uint32_t*>(row + n2.y) > n2.x;
+                o = 2u * o + (b2 ? 8u : 0u);
+                const uint2 n3 = *reinterpret_cast<const uint2*>(lw + c * (RK_LOWER * 8) + 32 + o);
+                const bool b3 = *reinterpret_cast<const uint32_t*>(row + n3.y) > n3.x;
+                o += b3 ? 4u : 0u;
+                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lv + c * (RK_LEAVES * 4) + o));
+            }
+        }
+        tbase += 3 * A;
+        lw += RK_LOWER * 8 * A;
+        lv += RK_LEAVES * 4 * A;
+    }
+}
+
 // One tree of the rank-form forest for one row: returns the leaf value.
 __device__ __forceinline__ float gbt_rank_tree(const unsigned char* __restrict__ row, const uint4 t4,
                                                const uint32_t* __restrict__ lw, const float* __restrict__ lv) {
@@ -224,4 +267,8 @@ struct gnx_gbt {
     const unsigned char* rank_forest;
     int use_rank;            // 1 = rank-form kernel when eligible (default), 0 = generic float traversal
     gnx::GbtTopC* h_topc;    // host copy of the top nodes for the parameter-bank variant (NULL if T too large)
+    gnx::GbtTopW* h_topw;    // wide-node variant: top nodes (parameter bank) ...
+    const unsigned char* wide_forest;  // ... and lower uint2 [T][12] | leaves [T][16] (shared-memory image)
+    size_t wide_forest_bytes;
+    int variant;             // rank-form flavour: 2 wide nodes (default when eligible), 1 narrow + parameter-bank tops, 0 narrow
 };
