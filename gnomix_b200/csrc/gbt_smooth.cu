@@ -325,7 +325,9 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
         for (int t = 0; t < n_trees; t++)
             for (int k = 0; k < 3; k++) m->h_topw->w[3 * t + k] = make_uint2(top[(size_t)t * 4 + k] & 0xffff0000u, top[(size_t)t * 4 + k] & 0xffffu);
     }
-    m->variant = m->h_topw ? 2 : (m->h_topc ? 1 : 0);
+    // measured on B200 (chr1 x 50 000): narrow + parameter-bank tops 59.6 ms, wide nodes 63.0 ms (LDS.64 costs two
+    // shared-memory wavefronts and the kernel is wavefront/issue co-limited) -> narrow is the default
+    m->variant = m->h_topc ? 1 : 0;
     if (const char* e = getenv("GNX_GBT_VARIANT")) {  // profiling / cross-check switch
         const int v = atoi(e);
         if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw)) m->variant = v;

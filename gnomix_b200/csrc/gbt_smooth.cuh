@@ -169,30 +169,33 @@ __device__ __forceinline__ void gbt_rank_walk_c(int A, const unsigned char* __re
 #pragma unroll
     for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
     int tbase = 0;
+    const unsigned char* lwb = reinterpret_cast<const unsigned char*>(lw);
+    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
 #pragma unroll 1
     for (int rd = 0; rd < rounds; rd++) {
 #pragma unroll
         for (int c = 0; c < AMAX; c++) {
             if (c < A) {
+                // the walk carries BYTE offsets into the level-2 / level-3 / leaf arrays: one select and
+                // one shift-add per level instead of index arithmetic
                 const uint32_t t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
                 const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (t0 & 0xffffu));
                 const bool b0 = x0 > t0;
                 const uint32_t n1 = b0 ? t2 : t1;
                 const uint32_t x1 = *reinterpret_cast<const uint32_t*>(row + (n1 & 0xffffu));
-                const bool b1 = x1 > n1;
-                const int i2 = (b0 ? 2 : 0) + (b1 ? 1 : 0);
-                const uint32_t n2 = lw[c * RK_LOWER + i2];
+                uint32_t o = (b0 ? 8u : 0u) + ((x1 > n1) ? 4u : 0u);
+                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(lwb + c * (RK_LOWER * 4) + o);
                 const uint32_t x2 = *reinterpret_cast<const uint32_t*>(row + (n2 & 0xffffu));
-                const int i3 = 2 * i2 + ((x2 > n2) ? 1 : 0);
-                const uint32_t n3 = lw[c * RK_LOWER + 4 + i3];
+                o = 2u * o + ((x2 > n2) ? 4u : 0u);
+                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(lwb + c * (RK_LOWER * 4) + 16 + o);
                 const uint32_t x3 = *reinterpret_cast<const uint32_t*>(row + (n3 & 0xffffu));
-                const int lf = 2 * i3 + ((x3 > n3) ? 1 : 0);
-                psum[c] = GNX_FADD(psum[c], lv[c * RK_LEAVES + lf]);
+                o = 2u * o + ((x3 > n3) ? 4u : 0u);
+                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
             }
         }
         tbase += 3 * A;
-        lw += RK_LOWER * A;
-        lv += RK_LEAVES * A;
+        lwb += RK_LOWER * 4 * A;
+        lvb += RK_LEAVES * 4 * A;
     }
 }
 

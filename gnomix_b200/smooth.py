@@ -59,14 +59,14 @@ class Smoother:
         import torch
         t = time()
         proba, _ = self._device_smooth(B, want_proba=True, want_label=False)
+        if self.calibrate:
+            if self.calibrator is None:
+                print("No calibrator found, returning original probabilities.")
+            else:
+                proba, _ = self.calibrator.transform_device(proba)   # K7, float64 as the reference returns
         if not (_is_torch(B) and B.is_cuda):
             torch.cuda.current_stream().synchronize()
             proba = proba.cpu().numpy()
-            if self.calibrate:
-                if self.calibrator is None:
-                    print("No calibrator found, returning original probabilities.")
-                else:
-                    proba = self.calibrator.transform(proba.reshape(-1, self.A)).reshape(-1, self.W, self.A)
         self.time["inference"] = time() - t
         return proba
 
@@ -76,8 +76,10 @@ class Smoother:
         _lib.require_gpu()
         import torch
         if self.calibrate and self.calibrator is not None:
-            return np.argmax(self.predict_proba(B), axis=-1)
-        _, label = self._device_smooth(B, want_proba=False, want_label=True)
+            proba, _ = self._device_smooth(B, want_proba=True, want_label=False)
+            _, label = self.calibrator.transform_device(proba, want_proba=False, want_label=True)
+        else:
+            _, label = self._device_smooth(B, want_proba=False, want_label=True)
         if _is_torch(B) and B.is_cuda:
             return label
         torch.cuda.current_stream().synchronize()

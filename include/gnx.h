@@ -36,6 +36,7 @@ typedef struct gnx_lr gnx_lr_t;   /* per-window logistic-regression base (K1) */
 typedef struct gnx_gbt gnx_gbt_t; /* gradient-boosted-tree smoother (K4)      */
 typedef struct gnx_crf gnx_crf_t; /* linear-chain CRF smoother (K5)           */
 typedef struct gnx_svc gnx_svc_t; /* CovRSK string-kernel SVC base (K2+K3)    */
+typedef struct gnx_cal gnx_cal_t; /* per-class isotonic calibrator (K7)        */
 
 int gnx_version(void);
 const char* gnx_last_error(void);
@@ -158,6 +159,24 @@ int gnx_svc_kernel_window(const gnx_svc_t* m, int w, const int8_t* X_dev, int64_
 int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float* B_dev,
                int64_t n_ind, int W, int max_it, int32_t* Y_dev, int32_t* tracker_dev,
                void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K7  Calibrator.transform on smoother probabilities (+ argmax)
+ * replaces: src/Smooth/Calibration.py:57-69 (per-class IsotonicRegression(out_of_bounds=
+ *           "clip").transform) and the normalisation of lines 24-39, as called from
+ *           src/Smooth/smooth.py:48-52.
+ * n_thr [A] thresholds per class; x_thr / y_thr the classes' X_thresholds_ / y_thresholds_
+ * concatenated (as float64); is_f32 = 1 if the fitted thresholds are float32 (a model
+ * fitted on the XGB smoother's float32 probabilities: scikit-learn then evaluates in
+ * float32), 0 for float64 (CRF smoother).  proba_dev [rows, A] float32 (in_is_f32) or
+ * float64; out_dev [rows, A] float64 and label_dev [rows] int32 (first maximum), either
+ * may be NULL.
+ * ------------------------------------------------------------------------- */
+int gnx_cal_model_create(gnx_cal_t** out, int A, int is_f32, const int32_t* n_thr,
+                         const double* x_thr, const double* y_thr);
+void gnx_cal_model_destroy(gnx_cal_t* m);
+int gnx_calibrate(const gnx_cal_t* m, const void* proba_dev, int in_is_f32, int64_t rows,
+                  double* out_dev, int32_t* label_dev, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Host-buffer pipeline: Gnomix.predict_proba / predict on a numpy-style host

@@ -22,6 +22,8 @@ What each file pins (reference file:line):
                     (src/Smooth/smooth.py:40-65) driven with the oracle's tree predictor as
                     smoother.model (xgboost itself is not installable here).
   meta.npz          get_meta_data (src/postprocess.py:25-67).
+  calibrator.npz    Calibrator.fit / transform (src/Smooth/Calibration.py:19-69) through
+                    scikit-learn IsotonicRegression.
 """
 from __future__ import annotations
 
@@ -278,6 +280,43 @@ def golden_vcf_to_npy(src):
     print("vcf_to_npy", X.shape, X.dtype, np.bincount(X.ravel()))
 
 
+def golden_calibrator(src):
+    """Calibrator.fit / transform (src/Smooth/Calibration.py:19-69) with scikit-learn's
+    IsotonicRegression: float32 probabilities (what the XGB smoother returns), float64
+    (the CRF smoother), and the binary case; queries include exact threshold hits, values outside
+    the fitted range (clip) and rows whose calibrated probabilities are all zero (NaN -> 1/A)."""
+    from src.Smooth.Calibration import Calibrator
+    out = {}
+    for tag, A, dt, seed in [("a7_f32", 7, np.float32, 11), ("a3_f64", 3, np.float64, 12), ("a2_f32", 2, np.float32, 13)]:
+        rng = np.random.default_rng(seed)
+        n = 4000
+        y = rng.integers(0, A, n)
+        p = rng.dirichlet(np.full(A, 0.4), n)
+        p[np.arange(n), y] += rng.random(n) * 1.5
+        p = (p / p.sum(1, keepdims=True)).astype(dt)
+        cal = Calibrator(A)
+        cal.fit(p, y)
+        q = rng.dirichlet(np.full(A, 0.3), (6, 50)).astype(dt)
+        thr = [(m.X_thresholds_, m.y_thresholds_) for m in cal.models]
+        for i in range(A):                       # exact hits, one ulp either side, out of range
+            xt = thr[i][0]
+            q[0, :8, i] = xt[rng.integers(0, len(xt), 8)]
+            q[1, :8, i] = np.nextafter(xt[rng.integers(0, len(xt), 8)], dt(2))
+            q[1, 8:16, i] = np.nextafter(xt[rng.integers(0, len(xt), 8)], dt(-1))
+        q[2, 0, :] = 0.0
+        q[2, 1, :] = 1.0
+        q[2, 2, :] = -0.5
+        q[2, 3, :] = 1.5
+        got = cal.transform(q.copy())
+        out["q_" + tag] = q
+        out["out_" + tag] = got
+        for i in range(A):
+            out["x_%s_%d" % (tag, i)] = thr[i][0]
+            out["y_%s_%d" % (tag, i)] = thr[i][1]
+        print("calibrator", tag, got.dtype, [len(t[0]) for t in thr], float(np.nanmin(got)), float(np.nanmax(got)))
+    np.savez_compressed(os.path.join(OUT, "calibrator.npz"), **out)
+
+
 def main():
     from oracle import refimport
     src = refimport.import_reference()
@@ -290,6 +329,7 @@ def main():
     golden_gnofix(src)
     golden_meta(src)
     golden_vcf_to_npy(src)
+    golden_calibrator(src)
 
 
 if __name__ == "__main__":

@@ -451,6 +451,86 @@ def multiclass_probability(k: int, r: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------
 # Row G: gnofix with the reference's defaults (src/Gnofix/gnofix.py:58-208,
 # src/Gnofix/phasing.py:182-198, called from src/model.py:188-214)
+# ----------------------------------------------------------------------------- calibrator
+# Calibrator.transform (reference src/Smooth/Calibration.py:57-69) with the normalisation of
+# lines 24-39.  Each class model is sklearn IsotonicRegression(out_of_bounds="clip"); its
+# transform (sklearn/isotonic.py::_transform) casts the input to the dtype of the fitted
+# thresholds, clips to [X_min_, X_max_], interpolates with scipy interp1d(kind="linear") and
+# casts back to that dtype.  interp1d delegates to numpy.interp when the thresholds are float64
+# (CRF smoother probabilities) and otherwise runs its own two-weight formula in the
+# thresholds' dtype (float32 thresholds = XGB smoother probabilities).
+
+def np_interp_restated(x, xp, fp):
+    """numpy.interp for x inside [xp[0], xp[-1]] (numpy/_core/src/multiarray/compiled_base.c,
+    arr_interp): j with xp[j] <= x < xp[j+1]; exact hit -> fp[j]; else
+    slope*(x - xp[j]) + fp[j] with slope = (fp[j+1]-fp[j])/(xp[j+1]-xp[j]), all float64."""
+    x = np.asarray(x, dtype=np.float64)
+    xp = np.asarray(xp, dtype=np.float64)
+    fp = np.asarray(fp, dtype=np.float64)
+    n = len(xp)
+    out = np.full(x.shape, np.nan)
+    ok = ~np.isnan(x)
+    xv = x[ok]
+    j = np.searchsorted(xp, xv, side="right") - 1
+    last = j >= n - 1
+    jj = np.clip(j, 0, max(n - 2, 0))
+    if n == 1:
+        res = np.full(xv.shape, fp[0])
+    else:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            slope = (fp[jj + 1] - fp[jj]) / (xp[jj + 1] - xp[jj])
+            res = slope * (xv - xp[jj]) + fp[jj]
+            alt = slope * (xv - xp[jj + 1]) + fp[jj + 1]
+        bad = np.isnan(res)
+        res = np.where(bad, alt, res)
+        res = np.where(np.isnan(res) & (fp[jj] == fp[jj + 1]), fp[jj], res)
+        res = np.where(xp[jj] == xv, fp[jj], res)
+        res = np.where(last, fp[n - 1], res)
+    out[ok] = res
+    return out
+
+
+def interp1d_linear_restated(x, xp, fp):
+    """scipy.interpolate.interp1d._call_linear in the arrays' own dtype (float32 here):
+    hi = clip(searchsorted(xp, x, 'left'), 1, n-1), lo = hi-1,
+    y = ((x - x_lo)/(x_hi - x_lo))*y_hi + ((x_hi - x)/(x_hi - x_lo))*y_lo."""
+    hi = np.clip(np.searchsorted(xp, x, side="left"), 1, len(xp) - 1)
+    lo = hi - 1
+    x_lo, x_hi, y_lo, y_hi = xp[lo], xp[hi], fp[lo], fp[hi]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return ((x - x_lo) / (x_hi - x_lo)) * y_hi + ((x_hi - x) / (x_hi - x_lo)) * y_lo
+
+
+def isotonic_transform(t, x_thr, y_thr):
+    """IsotonicRegression(out_of_bounds="clip").transform for fitted thresholds."""
+    dt = x_thr.dtype
+    t = np.asarray(t).astype(dt)
+    t = np.clip(t, x_thr[0], x_thr[-1])
+    if len(y_thr) == 1:
+        return np.repeat(y_thr, t.shape[0]).astype(dt)
+    if dt == np.float64 and y_thr.dtype == np.float64:
+        return np_interp_restated(t, x_thr, y_thr).astype(dt)
+    return interp1d_linear_restated(t, x_thr, y_thr.astype(dt)).astype(dt)
+
+
+def calibrator_transform(proba, thresholds):
+    """proba [..., A]; thresholds = [(X_thresholds_, y_thresholds_)] per class.  Returns float64."""
+    A = len(thresholds)
+    shape = proba.shape
+    flat = proba.reshape(-1, A)
+    iso = np.zeros((flat.shape[0], A))
+    for i, (xt, yt) in enumerate(thresholds):
+        iso[:, i] = isotonic_transform(flat[:, i], xt, yt)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if A == 2:
+            iso[:, 0] = 1. - iso[:, 1]
+        else:
+            iso /= np.sum(iso, axis=1)[:, np.newaxis]
+    iso[np.isnan(iso)] = 1. / A
+    iso[(1.0 < iso) & (iso <= 1.0 + 1e-5)] = 1.0
+    return iso.reshape(*shape)
+
+
 # ----------------------------------------------------------------------------
 
 

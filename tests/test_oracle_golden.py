@@ -181,3 +181,18 @@ def test_gnx_math_exp():
     got = np.array([lib.orc_expf_cr(float(v)) for v in xf], dtype=np.float32)
     want = np.exp(xf.astype(np.float64)).astype(np.float32)
     assert np.array_equal(got, want)
+
+
+def test_calibrator_restatement_matches_reference_calibrator():
+    """oracle calibrator_transform == the reference's Calibrator.transform (scikit-learn isotonic
+    models) bit for bit: float32 models (XGB smoother), float64 models (CRF smoother), binary."""
+    g = np.load(os.path.join(G, "calibrator.npz"))
+    for tag, A in [("a7_f32", 7), ("a3_f64", 3), ("a2_f32", 2)]:
+        thr = [(g["x_%s_%d" % (tag, i)], g["y_%s_%d" % (tag, i)]) for i in range(A)]
+        got = npo.calibrator_transform(g["q_" + tag], thr)
+        assert got.dtype == np.float64 and np.array_equal(got, g["out_" + tag]), tag
+    # numpy.interp restatement against numpy itself on awkward inputs
+    rng = np.random.default_rng(1)
+    xp = np.sort(rng.random(40)); fp = np.sort(rng.random(40))
+    x = np.concatenate([rng.random(500) * (xp[-1] - xp[0]) + xp[0], xp, [xp[0], xp[-1]]])
+    assert np.array_equal(npo.np_interp_restated(x, xp, fp), np.interp(x, xp, fp))
