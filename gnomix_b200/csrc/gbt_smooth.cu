@@ -148,6 +148,103 @@ gbt_smooth_rank_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
     }
 }
 
+// ---------------------------------------------------------------- tile variant (two kernels)
+// K4a: exact rank transform of the base probabilities, B f32 [n] -> R u16 [n]; NaN -> 0xFFFF.
+__global__ void __launch_bounds__(512)
+gbt_rank_u16_kernel(const float* __restrict__ thr, int K, int table_in_smem, const float* __restrict__ B, int64_t count,
+                    uint16_t* __restrict__ R) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float* tab = thr;
+    if (table_in_smem) {
+        float* t = reinterpret_cast<float*>(smem);
+        for (int i = threadIdx.x; i < K; i += blockDim.x) t[i] = __ldg(thr + i);
+        __syncthreads();
+        tab = t;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = __ldg(B + i);
+        int lo = 0, hi = K;  // #{j : tab[j] <= x}
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (tab[mid] <= x) lo = mid + 1; else hi = mid;
+        }
+        R[i] = (x != x) ? (uint16_t)0xFFFFu : (uint16_t)lo;
+    }
+}
+
+// K4b: tile = 32 haplotypes (lane = haplotype) x Lseg windows (warp = window); the rank tile is
+// lane-interleaved in shared memory (see gbt_rank_walk_t), the forest sits next to it.
+template <int AT>
+__global__ void __launch_bounds__(RK_THREADS, 1)
+gbt_smooth_tile_kernel(const __grid_constant__ GbtTopW topc, GbtDev m, const unsigned char* __restrict__ forest_img,
+                       size_t forest_bytes, const uint16_t* __restrict__ R, const float* __restrict__ B, int64_t N, int W,
+                       int nseg, int Lseg, float* __restrict__ proba, int32_t* __restrict__ label) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int A = AT ? AT : m.A;
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(forest_img);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
+    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * RK_LOWER * 4);
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem + forest_bytes);
+    const int pad = (m.S + 1) / 2;
+    const int Lslots = Lseg + m.S - 1;
+    const int rounds = m.T / A;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t nhb = (N + 31) / 32;
+    for (int64_t t = blockIdx.x; t < nhb * nseg; t += gridDim.x) {
+        const int64_t hb = t / nseg;
+        const int sg = (int)(t - hb * nseg);
+        const int64_t n = hb * 32 + lane;
+        const int w0 = sg * Lseg;
+        __syncthreads();
+        int saw_nan = 0;
+        for (int e = warp; e < Lslots * A; e += RK_THREADS / 32) {
+            const int jl = e / A, a = e - jl * A;
+            const int j = w0 + jl;
+            uint32_t r = 0;
+            if (n < N && j < W + m.S - 1) r = __ldg(R + (n * W + spad_to_orig(j, W, pad)) * A + a);
+            saw_nan |= (r == 0xFFFFu);
+            tile[e * 32 + lane] = r << 16;
+        }
+        const int slow = __syncthreads_or(saw_nan);
+        if (slow) {
+            // NaN inputs follow each node's default child: generic float traversal, one haplotype of the
+            // tile at a time, its padded float row staged where the rank tile was
+            float* bp = reinterpret_cast<float*>(tile);
+            for (int h = 0; h < 32; h++) {
+                const int64_t nh = hb * 32 + h;
+                if (nh >= N) break;
+                __syncthreads();
+                for (int e = threadIdx.x; e < Lslots * A; e += blockDim.x) {
+                    const int jl = e / A, a = e - jl * A;
+                    const int j = w0 + jl;
+                    bp[e] = (j < W + m.S - 1) ? __ldg(B + (nh * W + spad_to_orig(j, W, pad)) * A + a) : 0.f;
+                }
+                __syncthreads();
+                for (int wl = threadIdx.x; wl < Lseg && w0 + wl < W; wl += blockDim.x) {
+                    float psum[AMAX];
+                    gbt_eval_row<AT>(m, m.nodes, m.leaves, bp + (size_t)wl * A, psum);
+                    const int64_t row = nh * W + w0 + wl;
+                    gbt_finish<AT>(m, psum, proba ? proba + row * A : nullptr, label ? label + row : nullptr);
+                }
+            }
+            continue;
+        }
+        for (int wl = warp; wl < Lseg; wl += RK_THREADS / 32) {
+            const int w = w0 + wl;
+            if (w >= W) break;
+            const uint32_t row = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)(wl * A * 128 + lane * 4);
+            float psum[AMAX];
+            gbt_rank_walk_t<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
+            if (n < N) gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
+        }
+    }
+}
+
 // smoother.model.predict_proba(rows[k, F]) -- rows straight from global memory
 template <int AT>
 __global__ void gbt_rows_kernel(GbtDev m, const float* __restrict__ rows, int64_t k, float* __restrict__ proba) {
@@ -316,6 +413,34 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
         for (int t = 0; t < n_trees; t++)
             for (int k = 0; k < 3; k++) m->h_topc->w[3 * t + k] = top[(size_t)t * 4 + k];
     }
+    // tile image: the narrow image with the feature index in the low half of every node word
+    m->h_topt = nullptr;
+    m->tile_forest = nullptr;
+    m->tile_forest_bytes = 0;
+    if (rank_ok && n_trees <= GBT_TOPW_MAX_T && K <= 65534 && F <= 65535) {
+        std::vector<uint32_t> timg((size_t)n_trees * (RK_LOWER + RK_LEAVES), 0u);
+        m->h_topt = new GbtTopW();
+        auto conv = [&](uint32_t word) -> uint32_t {  // (k << 16 | byte offset in a row) -> (k << 16 | feature index)
+            const uint32_t off = (word & 0xffffu) / 4u, slot = off / (uint32_t)astride, a = off % (uint32_t)astride;
+            return (word & 0xffff0000u) | (slot * (uint32_t)A + a);
+        };
+        const uint32_t* lower = rimg.data();
+        const uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
+        for (size_t i = 0; i < (size_t)n_trees * RK_LOWER; i++) timg[i] = conv(lower[i]);
+        memcpy(timg.data() + (size_t)n_trees * RK_LOWER, rimg.data() + (size_t)n_trees * RK_LOWER, sizeof(uint32_t) * (size_t)n_trees * RK_LEAVES);
+        for (int t = 0; t < n_trees; t++)
+            for (int k = 0; k < 3; k++) {
+                const uint32_t wd = conv(top[(size_t)t * 4 + k]);
+                m->h_topt->w[3 * t + k] = make_uint2(wd & 0xffff0000u, (wd & 0xffffu) * 128u);
+            }
+        void* d_t = nullptr;
+        if (cudaMalloc(&d_t, timg.size() * 4) != cudaSuccess || cudaMemcpy(d_t, timg.data(), timg.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("gnx_gbt_model_create: tile image allocation failed");
+            return 1;
+        }
+        m->tile_forest = static_cast<const unsigned char*>(d_t);
+        m->tile_forest_bytes = timg.size() * 4;
+    }
     m->h_topw = nullptr;
     m->wide_forest = reinterpret_cast<const unsigned char*>(blob + forest + 256 + rb + tb);
     m->wide_forest_bytes = wb;
@@ -330,7 +455,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->variant = m->h_topc ? 1 : 0;
     if (const char* e = getenv("GNX_GBT_VARIANT")) {  // profiling / cross-check switch
         const int v = atoi(e);
-        if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw)) m->variant = v;
+        if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt)) m->variant = v;
     }
     *out = m;
     return 0;
@@ -339,6 +464,8 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
 void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     if (!m) return;
     if (m->d_blob) cudaFree(m->d_blob);
+    if (m->tile_forest) cudaFree(const_cast<unsigned char*>(m->tile_forest));
+    delete m->h_topt;
     delete m->h_topw;
     delete m->h_topc;
     delete m;
@@ -367,12 +494,44 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bp_bytes = (size_t)(W + 2 * pad) * m->d.A * sizeof(float);
     const size_t smem_max = 227 * 1024;
+    if (m->d.rank_ok && m->use_rank && m->variant == 3 && m->h_topt) {
+        // tile variant: K4a rank transform into a stream-ordered scratch buffer, K4b tile kernel
+        const size_t slot_bytes = (size_t)m->d.A * 128;
+        const size_t room = smem_max - m->tile_forest_bytes - 16;
+        const int Lmax = (int)std::min<int64_t>((int64_t)(room / slot_bytes) - (m->d.S - 1), 2 * (RK_THREADS / 32));
+        if (Lmax >= 32 || Lmax >= W) {
+            const int nseg = (int)ceil_div(W, std::min(Lmax, W));
+            const int Lseg = (int)ceil_div(W, nseg);
+            const size_t smem = m->tile_forest_bytes + (size_t)(Lseg + m->d.S - 1) * slot_bytes + 16;
+            const int64_t count = N * (int64_t)W * m->d.A;
+            uint16_t* R = nullptr;
+            GNX_CUDA(cudaMallocAsync((void**)&R, (size_t)count * sizeof(uint16_t), st));
+            const int in_smem = (size_t)m->d.K * 4 <= 160 * 1024;
+            const size_t rsm = in_smem ? (size_t)m->d.K * 4 : 0;
+            GNX_CUDA(cudaFuncSetAttribute(gbt_rank_u16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
+            gbt_rank_u16_kernel<<<(int)std::min<int64_t>(ceil_div(count, 512), (int64_t)sm_count() * 4), 512, rsm, st>>>(
+                m->d.thr_table, m->d.K, in_smem, B_dev, count, R);
+            const int64_t tiles = ceil_div(N, 32) * nseg;
+            const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count());
+#define CALLT(AT)                                                                                                              \
+    do {                                                                                                                       \
+        GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        gbt_smooth_tile_kernel<AT><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, m->tile_forest, m->tile_forest_bytes, R, \
+                                                                   B_dev, N, W, nseg, Lseg, proba_dev, label_dev);             \
+    } while (0)
+            GBT_DISPATCH_A(m->d.A, CALLT)
+#undef CALLT
+            GNX_CUDA(cudaGetLastError());
+            GNX_CUDA(cudaFreeAsync(R, st));
+            return 0;
+        }
+    }
     if (m->d.rank_ok && m->use_rank) {
         // fast path: units of (haplotype, segment of Lseg windows), G units per CTA pass.  One segment
         // per haplotype when the chromosome fits shared memory; (G, Lseg) chosen for the best fit of
         // rows to the 1024 threads.
         const size_t slot_bytes = (size_t)m->d.astride * 4;
-        const int var = m->variant;
+        const int var = m->variant == 3 ? (m->h_topc ? 1 : 0) : m->variant;  // tile variant not applicable here
         const size_t img_bytes = (var == 2) ? m->wide_forest_bytes : m->rank_forest_bytes;
         const unsigned char* img = (var == 2) ? m->wide_forest : m->rank_forest;
         const size_t room = smem_max - img_bytes - 16;
@@ -440,12 +599,12 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
 
 int gnx_gbt_set_kernel(gnx_gbt_t* m, int which) {
     GNX_REQUIRE(m != nullptr, "gnx_gbt_set_kernel: NULL model");
-    GNX_REQUIRE(which == 0 || which == 1 || (which >= 10 && which <= 12), "gnx_gbt_set_kernel: unknown kernel %d", which);
+    GNX_REQUIRE(which == 0 || which == 1 || (which >= 10 && which <= 13), "gnx_gbt_set_kernel: unknown kernel %d", which);
     if (which >= 10) {  // rank-form flavour: 10 narrow nodes, 11 narrow + parameter-bank tops, 12 wide nodes
         const int v = which - 10;
         m->use_rank = 1;
         if (!m->d.rank_ok) return 0;  // not a rank-form forest: the generic kernel runs whatever the flavour
-        GNX_REQUIRE(v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw), "gnx_gbt_set_kernel: flavour %d not available for this forest", v);
+        GNX_REQUIRE(v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt), "gnx_gbt_set_kernel: flavour %d not available for this forest", v);
         m->variant = v;
         m->use_rank = 1;
         return 0;

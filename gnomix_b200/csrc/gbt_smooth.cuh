@@ -199,15 +199,61 @@ __device__ __forceinline__ void gbt_rank_walk_c(int A, const unsigned char* __re
     }
 }
 
+constexpr int GBT_TOPW_MAX_T = 1024;
+struct GbtTopW {
+    uint2 w[3 * GBT_TOPW_MAX_T];
+};
+
+// Tile variant (gbt_smooth_tile_kernel): the rank tile is lane-interleaved, word ((slot * A + a) * 32 + lane)
+// with lane = haplotype, so a feature load hits bank `lane` whatever node each lane is at (no bank
+// conflicts under divergence).  Top three nodes of every tree: two words { k << 16, feat * 128 } in the
+// kernel parameter bank (no mask, no shared-memory wavefront); nodes 3..14: one word (k << 16) | feat
+// in shared memory (an 8-byte node would cost a second wavefront per load).
+__device__ __forceinline__ uint32_t gnx_lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+template <int AT>
+__device__ __forceinline__ void gbt_rank_walk_t(int A, uint32_t row, const GbtTopW& top, const uint32_t* __restrict__ lw,
+                                                const float* __restrict__ lv, int rounds, float* psum) {
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+    int tbase = 0;
+    const unsigned char* lwb = reinterpret_cast<const unsigned char*>(lw);
+    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const uint2 t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
+                const bool b0 = gnx_lds_u32(row + t0.y) > t0.x;
+                const uint2 n1 = b0 ? t2 : t1;
+                const bool b1 = gnx_lds_u32(row + n1.y) > n1.x;
+                uint32_t o = (b0 ? 8u : 0u) + (b1 ? 4u : 0u);
+                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(lwb + c * (RK_LOWER * 4) + o);
+                const bool b2 = gnx_lds_u32(row + ((n2 & 0xffffu) << 7)) > n2;
+                o = 2u * o + (b2 ? 4u : 0u);
+                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(lwb + c * (RK_LOWER * 4) + 16 + o);
+                const bool b3 = gnx_lds_u32(row + ((n3 & 0xffffu) << 7)) > n3;
+                o = 2u * o + (b3 ? 4u : 0u);
+                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
+            }
+        }
+        tbase += 3 * A;
+        lwb += RK_LOWER * 4 * A;
+        lvb += RK_LEAVES * 4 * A;
+    }
+}
+
 // Wide-node variant (default of gbt_smooth): every node is two words { k << 16, byte offset of the
 // feature in a row }, so the feature address is one add (no mask) and the walk carries BYTE offsets
 // into the level-2 / level-3 / leaf arrays (select + shift-add per level instead of index arithmetic).
 // Top three nodes of every tree in the kernel parameter bank, nodes 3..14 (uint2) and leaves in
 // shared memory: 160 B per tree.
-constexpr int GBT_TOPW_MAX_T = 1024;
-struct GbtTopW {
-    uint2 w[3 * GBT_TOPW_MAX_T];
-};
 
 template <int AT>
 __device__ __forceinline__ void gbt_rank_walk_w(int A, const unsigned char* __restrict__ row, const GbtTopW& top,
@@ -273,5 +319,8 @@ struct gnx_gbt {
     gnx::GbtTopW* h_topw;    // wide-node variant: top nodes (parameter bank) ...
     const unsigned char* wide_forest;  // ... and lower uint2 [T][12] | leaves [T][16] (shared-memory image)
     size_t wide_forest_bytes;
+    gnx::GbtTopW* h_topt;    // tile variant: top nodes { k << 16, feat * 128 } (parameter bank) ...
+    const unsigned char* tile_forest;  // ... and lower u32 [T][12] | leaves [T][16], node = (k << 16) | feat
+    size_t tile_forest_bytes;
     int variant;             // rank-form flavour: 2 wide nodes (default when eligible), 1 narrow + parameter-bank tops, 0 narrow
 };
