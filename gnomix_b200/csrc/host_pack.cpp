@@ -233,6 +233,16 @@ static Pool* pool(int threads) {
     return g_pool;
 }
 
+void parallel_for(int64_t items, int threads, const std::function<void(int64_t)>& fn) {
+    if (threads <= 0) threads = host_threads_default();
+    if (threads == 1 || items <= 1) {
+        for (int64_t i = 0; i < items; i++) fn(i);
+        return;
+    }
+    std::lock_guard<std::mutex> l(g_pool_mu);
+    pool(threads)->run(items, fn);
+}
+
 int pack_rows(const int8_t* X, int64_t n, int64_t ldX, int64_t C, uint64_t* out, int64_t out_pitch_words, int threads,
               int* isa) {
     int which = 0;
@@ -250,12 +260,7 @@ int pack_rows(const int8_t* X, int64_t n, int64_t ldX, int64_t C, uint64_t* out,
         for (int64_t r = b * rows_per; r < r1; r++) local |= fn(X + r * ldX, C, out + r * out_pitch_words, groups);
         if (local) bad.fetch_or(local, std::memory_order_relaxed);
     };
-    if (threads == 1 || blocks == 1) {
-        for (int64_t b = 0; b < blocks; b++) job(b);
-    } else {
-        std::lock_guard<std::mutex> l(g_pool_mu);
-        pool(threads)->run(blocks, job);
-    }
+    parallel_for(blocks, threads, job);
     return bad.load() ? 1 : 0;
 }
 

@@ -4,6 +4,8 @@
 
 #include <stdint.h>
 
+#include <functional>
+
 namespace gnx {
 
 // Packs rows [0, n) of X (int8 [n, ldX], C valid columns) into out (row pitch
@@ -14,5 +16,8 @@ namespace gnx {
 int pack_rows(const int8_t* X, int64_t n, int64_t ldX, int64_t C, uint64_t* out, int64_t out_pitch_words, int threads,
               int* isa);
 int host_threads_default();
+// Runs fn(0) .. fn(items - 1) on the library's persistent host worker pool (`threads` <= 0: default count);
+// returns when all are done.  One job at a time.
+void parallel_for(int64_t items, int threads, const std::function<void(int64_t)>& fn);
 
 }  // namespace gnx

@@ -88,21 +88,29 @@ def write_msp(msp_prefix, meta_data, pred_labels, populations, query_samples):
 
 
 def write_fb(fb_prefix, meta_data, proba, ancestry, query_samples):
-    """src/postprocess.py:100-126 (same header, same shortest-repr number formatting)."""
+    """src/postprocess.py:100-126 (same header, same shortest-repr number formatting).  The body --
+    one line per window with N*A probabilities as text -- is formatted by the library's host
+    threads (gnx_write_fb_body, csrc/host_io.cpp) instead of one Python object per number."""
+    import ctypes as C
+    from . import _lib
     proba = np.asarray(proba)
+    if proba.dtype not in (np.float32, np.float64):
+        proba = proba.astype(np.float64)
+    proba = np.ascontiguousarray(proba)
     n_rows = meta_data.shape[0]
+    N, W, A = proba.shape
+    assert W == n_rows, "proba has %d windows, the window table %d" % (W, n_rows)
     pp = np.round(np.mean(np.array(meta_data[["spos", "epos"]], dtype=int), axis=1)).astype(int)
     gp = np.mean(np.array(meta_data[["sgpos", "egpos"]], dtype=float), axis=1).astype(float)
     chm = np.asarray(meta_data["chm"]).astype(str)
     header = ["chromosome", "physical position", "genetic_position", "genetic_marker_index"]
     header += [":::".join([q, h, a]) for q in query_samples for h in ["hap1", "hap2"] for a in ancestry]
-    fb_prob = np.swapaxes(proba, 1, 2).reshape(-1, n_rows).T           # [W, N*A], as the reference
-    with open(fb_prefix + ".fb", "w") as f:
+    path = fb_prefix + ".fb"
+    with open(path, "w") as f:
         f.write("#reference_panel_population:\t")
         f.write("\t".join(ancestry) + "\n")
         f.write("\t".join(header) + "\n")
-        for l in range(n_rows):
-            f.write("\t".join([chm[l], str(pp[l]), repr(float(gp[l])), "."]))
-            f.write("\t")
-            f.write("\t".join(fb_prob[l].astype(str)))
-            f.write("\n")
+    prefixes = [("\t".join([chm[l], str(pp[l]), repr(float(gp[l])), "."]) + "\t").encode() for l in range(n_rows)]
+    arr = (C.c_char_p * n_rows)(*prefixes)
+    _lib.check(_lib.lib().gnx_write_fb_body(path.encode(), 1, proba.ctypes.data, int(proba.dtype == np.float64), N, W, A,
+                                            C.cast(arr, C.c_void_p), 0), "gnx_write_fb_body")

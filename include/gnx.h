@@ -215,6 +215,18 @@ int gnx_infer_host_rates(double* pack_gbs, double* h2d_gbs);
 /* what the last gnx_infer_host call moved: packed fraction of each chunk's rows, bytes
  * copied host->device and device->host */
 int gnx_infer_host_last_transfer(double* frac, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* ---------------------------------------------------------------------------
+ * Host-side output of run_inference: body of the .fb file
+ * replaces: the per-window formatting loop of src/postprocess.py:100-126 (write_fb).
+ * Appends (append != 0) or writes W lines to `path`: line l = prefixes[l] followed by the
+ * tab-separated str(proba[n, l, a]) (n outer, a inner; numpy's shortest round-trip float
+ * formatting, float32 or float64 per is_f64) and a newline.  proba row-major [N, W, A] host
+ * memory.  Lines are formatted on `threads` host threads (<= 0: gnx_host_threads()).
+ * gnx_format_floats is the formatter alone (newline-separated; returns the length or -1).
+ * ------------------------------------------------------------------------- */
+int gnx_write_fb_body(const char* path, int append, const void* proba, int is_f64, int64_t N,
+                      int64_t W, int64_t A, const char* const* prefixes, int threads);
+int64_t gnx_format_floats(const void* values, int is_f64, int64_t n, char* out, int64_t cap);
 /* host threads the library uses (cores this process may run on, or GNX_HOST_THREADS) */
 int gnx_host_threads(void);
 

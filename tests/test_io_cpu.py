@@ -104,3 +104,41 @@ def test_genetic_map_reader(tmp_path):
     p.write_text("chr22\t100\t0.0\nchr22\t200\t0.5\nchr1\t10\t0.1\n")
     df = gio.read_genetic_map(str(p), chm="22")
     assert df["pos"].tolist() == [100, 200] and df["pos_cm"].tolist() == [0.0, 0.5]
+
+
+def test_write_fb_native_body_matches_numpy_formatting(tmp_path):
+    """gnx_write_fb_body (csrc/host_io.cpp) against the reference's per-number numpy str formatting
+    (src/postprocess.py:112-126) on awkward values, both dtypes, several thread counts."""
+    import pandas as pd
+    from gnomix_b200 import postprocess as pp, _lib
+    rng = np.random.default_rng(5)
+    N, W, A = 14, 9, 3
+    meta = pd.DataFrame(np.array([["7"] * W, np.arange(W) * 1000 + 5, np.arange(W) * 1000 + 900, np.round(np.arange(W) * 0.2, 5),
+                                  np.round(np.arange(W) * 0.2 + 0.19, 5), np.full(W, 857)]).T,
+                        columns=["chm", "spos", "epos", "sgpos", "egpos", "n snps"])
+    pops, samples = ["AFR", "EUR", "EAS"], ["S%d" % i for i in range(N // 2)]
+    for dt in (np.float32, np.float64):
+        proba = rng.dirichlet(np.full(A, 0.2), (N, W)).astype(dt)
+        proba[0, 0] = [0.0, 1.0, 1e-4]
+        proba[1, 0] = [1e-5, 9.9999e-5, 0.5]
+        proba[2, 1] = [1e-30, 1.0 / 3.0, 2.0 / 3.0]
+        proba[3, 2] = [np.nan, 1e6, 123456.7]
+        for th in ("1", "3", ""):
+            if th:
+                os.environ["GNX_HOST_THREADS"] = th
+            else:
+                os.environ.pop("GNX_HOST_THREADS", None)
+            pp.write_fb(str(tmp_path / "n"), meta, proba, pops, samples)
+            lines = open(tmp_path / "n.fb").read().split("\n")
+            assert len(lines) == W + 3 and lines[-1] == ""
+            fb_prob = np.swapaxes(proba, 1, 2).reshape(-1, W).T          # the reference's [W, N*A] view
+            for l in range(W):
+                assert lines[2 + l].split("\t")[4:] == list(fb_prob[l].astype(str)), (dt, th, l)
+    # the float formatter alone, wide range
+    v = np.concatenate([10.0 ** rng.uniform(-40, 30, 5000) * rng.choice([-1, 1], 5000), rng.random(5000), [0.0, -0.0, 1e16, 1e-4, 999999.94, 1e6]])
+    for dt in (np.float32, np.float64):
+        a = np.ascontiguousarray(v.astype(dt))
+        import ctypes as C
+        out = C.create_string_buffer(a.size * 34 + 8)
+        n = _lib.lib().gnx_format_floats(a.ctypes.data, int(dt == np.float64), a.size, out, len(out))
+        assert out.raw[:n].decode().split("\n")[:-1] == list(a.astype(str))
