@@ -172,9 +172,10 @@ extern "C" int gnx_infer_host(const gnx_lr_t* lr, const gnx_gbt_t* gbt, const in
     const int W = lr->d.W, A = lr->d.A;
     const int64_t pitch = (C + 127) & ~int64_t(127);
     const bool pack = env_pack_enabled();
-    // ~2 GB of X per slot unpacked; ~1.25 GB when packing (finer chunks: the host pack of chunk i+1
-    // is what overlaps the transfer + kernels of chunk i)
-    const int64_t target = pack ? (int64_t(5) << 28) : (int64_t(1) << 31);
+    // ~2 GB of X per slot unpacked; ~0.6 GB when packing (finer chunks: the host pack of chunk i+1 is what
+    // overlaps the transfer + kernels of chunk i, and the first pack / last kernels are not overlapped at all;
+    // measured on chr1 x 16 384 haplotypes: 83.0k hap/s at 256-768 haplotypes per chunk, 79.8k at 1024-2048)
+    const int64_t target = pack ? (int64_t(5) << 27) : (int64_t(1) << 31);
     int64_t chunk = chunk_haps > 0 ? chunk_haps : std::max<int64_t>(256, target / pitch / 256 * 256);
     chunk = std::min<int64_t>(chunk, (N + 255) / 256 * 256);
     const int64_t pitch_words = pitch / 32;  // 2 x u64 per 64 SNPs

@@ -16,11 +16,11 @@ Xpage = Xpin.numpy().copy()
 Lh = torch.empty((n, W), dtype=torch.int32, pin_memory=True)
 lib = _lib.lib(); hlr, hgbt = base.handle(), smooth.model.handle(S)
 print("host threads", lib.gnx_host_threads(), flush=True)
-def run(ptr, tag, steps=2):
-    _lib.check(lib.gnx_infer_host(hlr, hgbt, ptr, n, ld, None, Lh.data_ptr(), 0)); torch.cuda.synchronize()
+def run(ptr, tag, steps=2, chunk=0):
+    _lib.check(lib.gnx_infer_host(hlr, hgbt, ptr, n, ld, None, Lh.data_ptr(), chunk)); torch.cuda.synchronize()
     t = time.perf_counter()
     for _ in range(steps):
-        _lib.check(lib.gnx_infer_host(hlr, hgbt, ptr, n, ld, None, Lh.data_ptr(), 0))
+        _lib.check(lib.gnx_infer_host(hlr, hgbt, ptr, n, ld, None, Lh.data_ptr(), chunk))
     torch.cuda.synchronize(); dt = (time.perf_counter() - t) / steps
     f, h, d = C.c_double(0), C.c_int64(0), C.c_int64(0)
     lib.gnx_infer_host_last_transfer(C.byref(f), C.byref(h), C.byref(d))
@@ -42,3 +42,7 @@ for fr in ("0.3", "0.45", "0.6", "0.75", "0.9", "1"):
     assert torch.equal(run(Xpin.data_ptr(), "pinned frac=" + fr), ref)
 os.environ["GNX_HOST_PACK_FRAC"] = "1"
 assert torch.equal(run(Xpage.ctypes.data, "pageable frac=1"), ref)
+del os.environ["GNX_HOST_PACK_FRAC"]
+for ch in (256, 512, 768, 1024, 2048):
+    assert torch.equal(run(Xpin.data_ptr(), "pinned auto chunk=%d" % ch, chunk=ch), ref)
+    assert torch.equal(run(Xpage.ctypes.data, "pageable chunk=%d" % ch, chunk=ch), ref)
