@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--haps", type=int, default=50_000, help="haplotypes per GPU")
-    ap.add_argument("--e2e-haps", type=int, default=8192)
+    ap.add_argument("--e2e-haps", type=int, default=16384)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-haps", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")

@@ -38,7 +38,8 @@ struct Workspace {
     size_t x_bytes = 0, b_bytes = 0, p_bytes = 0, l_bytes = 0, pk_bytes = 0;
     double pack_gbs = 0.0, h2d_gbs = 0.0;      // calibrated host pack / pinned H2D rates (GB/s of int8 / of bytes)
     int calib_threads = 0;
-    double last_frac = 0.0;                    // what the last gnx_infer_host call did
+    double frac_hint = 0.0;                    // packed fraction the feedback loop of the last call settled on
+    double last_frac = 0.0;                    // what the last gnx_infer_host call did (average over its chunks)
     int64_t last_h2d = 0, last_d2h = 0;
     int8_t* X[2] = {nullptr, nullptr};
     float* B[2] = {nullptr, nullptr};
@@ -187,40 +188,60 @@ extern "C" int gnx_infer_host(const gnx_lr_t* lr, const gnx_gbt_t* gbt, const in
     const int threads = host_threads_default();
     // fraction of each chunk's rows that is packed by the cores (the rest crosses the bus raw)
     double frac = 0.0;
+    bool adapt = false;  // feedback on the fraction: pack more when the host waits for the bus, less when it never does
     if (pack) {
         frac = 1.0;
         const char* fe = getenv("GNX_HOST_PACK_FRAC");
         if (fe && *fe) {
             frac = std::min(1.0, std::max(0.0, atof(fe)));
         } else if (is_pinned(X_host)) {
-            if (ws.pack_gbs <= 0.0 || ws.calib_threads != threads)
+            if (ws.pack_gbs <= 0.0 || ws.calib_threads != threads) {
                 if (calibrate(ws, X_host, N, ldX, C, pitch_words, threads)) return 1;
+                ws.frac_hint = 0.0;
+            }
             if (ws.pack_gbs > 0.0 && ws.h2d_gbs > 0.0) {
                 // the cores lose some memory bandwidth to the concurrent DMA reads: derate P
-                frac = 1.0 / (ws.h2d_gbs / (0.85 * ws.pack_gbs) + 0.75);
-                if (frac > 0.92) frac = 1.0;
+                frac = ws.frac_hint > 0.0 ? ws.frac_hint : 1.0 / (ws.h2d_gbs / (0.85 * ws.pack_gbs) + 0.75);
+                adapt = true;
             }
         }
     }
-    // results of the chunk that last used slot s: copied out of the pinned staging once its D2H finished
+    // Results: D2H straight into the caller's buffers when they are pinned; otherwise into pinned staging,
+    // copied out by the worker pool once the chunk's D2H has finished (a single-threaded memcpy of the labels
+    // would be ~15 % of the per-chunk host time).
+    const bool lab_direct = is_pinned(label_host), proba_direct = proba_host && is_pinned(proba_host);
     int64_t pend_n0[2] = {0, 0}, pend_n[2] = {0, 0};
+    auto copy_out = [&](char* dst, const char* src, size_t bytes) {
+        const size_t blk = size_t(1) << 20;
+        const int64_t nb = (int64_t)((bytes + blk - 1) / blk);
+        parallel_for(nb, threads, [&](int64_t b) {
+            const size_t o = (size_t)b * blk;
+            memcpy(dst + o, src + o, std::min(blk, bytes - o));
+        });
+    };
     auto drain = [&](int s) -> int {
         if (pend_n[s] == 0) return 0;
         GNX_CUDA(cudaEventSynchronize(ws.out_done[s]));
-        memcpy(label_host + pend_n0[s] * W, ws.Lh[s], (size_t)pend_n[s] * W * sizeof(int32_t));
-        if (proba_host) memcpy(proba_host + pend_n0[s] * W * A, ws.Ph[s], (size_t)pend_n[s] * W * A * sizeof(float));
+        if (!lab_direct)
+            copy_out(reinterpret_cast<char*>(label_host + pend_n0[s] * W), reinterpret_cast<const char*>(ws.Lh[s]),
+                     (size_t)pend_n[s] * W * sizeof(int32_t));
+        if (proba_host && !proba_direct)
+            copy_out(reinterpret_cast<char*>(proba_host + pend_n0[s] * W * A), reinterpret_cast<const char*>(ws.Ph[s]),
+                     (size_t)pend_n[s] * W * A * sizeof(float));
         pend_n[s] = 0;
         return 0;
     };
     bool stage_used[kStage] = {};
     int it = 0;
-    ws.last_frac = frac;
+    ws.last_frac = 0.0;
     ws.last_h2d = ws.last_d2h = 0;
+    int64_t rows_packed = 0;
     for (int64_t n0 = 0; n0 < N; n0 += chunk, it++) {
         const int s = it & 1, hs = it % kStage;
         const int64_t n = std::min(chunk, N - n0);
         cudaStream_t st = ws.st[s];
         int64_t np = frac >= 1.0 ? n : (int64_t)(frac * (double)n);  // rows [0, np) packed, [np, n) raw
+        double wait_s = 0.0, pack_s = 0.0, t0;
         // raw part first: the DMA engine moves it while the cores pack the rest
         if (np < n) ws.last_h2d += (n - np) * C;
         if (np < n)
@@ -228,10 +249,21 @@ extern "C" int gnx_infer_host(const gnx_lr_t* lr, const gnx_gbt_t* gbt, const in
                                        (size_t)(n - np), cudaMemcpyHostToDevice, st));
         bool packed = false;
         if (np > 0) {
+            t0 = now_s();
             if (stage_used[hs]) GNX_CUDA(cudaEventSynchronize(ws.h2d_done[hs]));
+            wait_s += now_s() - t0;
+            t0 = now_s();
             packed = pack_rows(X_host + n0 * ldX, np, ldX, C, ws.stage[hs], pitch_words, threads, nullptr) == 0;
+            pack_s = now_s() - t0;
+            if (packed) rows_packed += np;
         }
+        t0 = now_s();
         if (drain(s)) return 1;  // slot s is about to be overwritten (stream order covers the device side)
+        wait_s += now_s() - t0;
+        if (adapt && it >= 2) {
+            if (wait_s > 0.15 * pack_s) frac = std::min(1.0, frac + 0.04);
+            else if (wait_s < 0.03 * pack_s) frac = std::max(0.05, frac - 0.02);
+        }
         if (packed) {
             GNX_CUDA(cudaMemcpyAsync(ws.PK[s], ws.stage[hs], (size_t)np * pitch_words * 8, cudaMemcpyHostToDevice, st));
             GNX_CUDA(cudaEventRecord(ws.h2d_done[hs], st));
@@ -245,14 +277,18 @@ extern "C" int gnx_infer_host(const gnx_lr_t* lr, const gnx_gbt_t* gbt, const in
         }
         if (gnx_lr_predict(lr, ws.X[s], n, pitch, ws.B[s], st)) return 1;
         if (gnx_gbt_smooth(gbt, ws.B[s], n, W, proba_host ? ws.P[s] : nullptr, ws.Lb[s], st)) return 1;
-        GNX_CUDA(cudaMemcpyAsync(ws.Lh[s], ws.Lb[s], (size_t)n * W * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        GNX_CUDA(cudaMemcpyAsync(lab_direct ? label_host + n0 * W : ws.Lh[s], ws.Lb[s], (size_t)n * W * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, st));
         if (proba_host)
-            GNX_CUDA(cudaMemcpyAsync(ws.Ph[s], ws.P[s], (size_t)n * W * A * sizeof(float), cudaMemcpyDeviceToHost, st));
+            GNX_CUDA(cudaMemcpyAsync(proba_direct ? proba_host + n0 * W * A : ws.Ph[s], ws.P[s], (size_t)n * W * A * sizeof(float),
+                                     cudaMemcpyDeviceToHost, st));
         GNX_CUDA(cudaEventRecord(ws.out_done[s], st));
         ws.last_d2h += n * W * (int64_t)sizeof(int32_t) + (proba_host ? n * W * A * (int64_t)sizeof(float) : 0);
         pend_n0[s] = n0;
         pend_n[s] = n;
     }
+    ws.last_frac = (double)rows_packed / (double)N;
+    if (adapt && it >= 8) ws.frac_hint = frac;
     // the older pending chunk first
     if (drain(it & 1)) return 1;
     if (drain((it & 1) ^ 1)) return 1;
