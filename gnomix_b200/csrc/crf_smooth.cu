@@ -13,6 +13,7 @@
 // pass parks the unnormalised alpha row in the output buffer; the backward pass re-derives
 // the scale factor from it (same sum, same order) and overwrites it with the marginal.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -143,6 +144,137 @@ crf_smooth_kernel(CrfDev m, const double* __restrict__ B, int64_t N, int W, doub
     }
 }
 
+// Lane-parallel variant (L, A <= 8): 8 lanes per haplotype, lane y owns label y.  Every output element is
+// produced by exactly the operation sequence of the kernel above (sums run over i / y / a in the same
+// order, operands fetched from the owning lanes with shuffles), so results are bit-identical; the chain
+// per step shrinks from L*L to L multiply-adds and one exp, and 8x more threads hide the latency.
+// Global memory is touched in bursts of CRF_TB steps per haplotype (staged in shared memory): a haplotype's
+// rows are contiguous in t, but one 56-byte row per haplotype per step across 20 000 concurrent haplotypes
+// is a DRAM row miss every time (the first version of this kernel ran no faster than thread-per-haplotype).
+constexpr int CRF_TB = 16;
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__global__ void __launch_bounds__(128)
+crf_smooth_lanes_kernel(CrfDev m, const double* __restrict__ B, int64_t N, int W, double* __restrict__ proba,
+                        int32_t* __restrict__ label) {
+    __shared__ double s_b[16][CRF_TB * 8];     // base probabilities of the chunk, [tt][a] dense (stride A)
+    __shared__ double s_o[16][CRF_TB * 8];     // alpha rows / marginals of the chunk, [tt][y] dense (stride L)
+    __shared__ int32_t s_l[16][CRF_TB];
+    const int A = m.A, L = m.L;
+    const int lane = threadIdx.x & 31, y = lane & 7, g0 = lane & ~7, grp = threadIdx.x >> 3;
+    const int64_t n_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool live = n_raw < N;
+    const int64_t n = live ? n_raw : N - 1;          // idle groups shadow the last haplotype, stores masked
+    const int yy = (y < L) ? y : L - 1;               // idle lanes shadow the last label
+    const double* b = B + n * (int64_t)W * A;
+    double* out = proba + n * (int64_t)W * L;
+    double* sb = s_b[grp];
+    double* so = s_o[grp];
+    int32_t* sl = s_l[grp];
+    double sw[8], etc[8], etr[8];                     // state_w[:, y], exp_trans[:, y], exp_trans[y, :]
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        sw[k] = (k < A) ? m.state_w[k * L + yy] : 0.0;
+        etc[k] = (k < L) ? m.exp_trans[k * L + yy] : 0.0;
+        etr[k] = (k < L) ? m.exp_trans[yy * L + k] : 0.0;
+    }
+    auto exp_state = [&](int tt) {
+        double st = 0.0;
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+            if (a < A) st = GNX_ADD(st, GNX_MUL(sb[tt * A + a], sw[a]));
+        return gnx_exp(st);
+    };
+    auto row_scale = [&](double mine) {              // 1 / sum_y cur[y], summed in label order
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double v = shfl_d(mine, g0 + k);
+            if (k < L) sum = GNX_ADD(sum, v);
+        }
+        return (sum != 0.0) ? GNX_DIV(1.0, sum) : 1.0;
+    };
+
+    // ---- forward
+    double al = 0.0;
+    for (int t0 = 0; t0 < W; t0 += CRF_TB) {
+        const int nt = min(CRF_TB, W - t0);
+        for (int i = y; i < nt * A; i += 8) sb[i] = __ldg(b + (int64_t)t0 * A + i);
+        __syncwarp();
+        for (int tt = 0; tt < nt; tt++) {
+            const double es = exp_state(tt);
+            double cur;
+            if (t0 + tt == 0) {
+                cur = es;
+            } else {
+                cur = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const double ai = shfl_d(al, g0 + i);
+                    if (i < L) cur = GNX_ADD(cur, GNX_MUL(ai, etc[i]));
+                }
+                cur = GNX_MUL(cur, es);
+            }
+            const double sc = row_scale(cur);
+            al = GNX_MUL(cur, sc);
+            if (y < L) so[tt * L + y] = cur;
+        }
+        __syncwarp();
+        if (live)
+            for (int i = y; i < nt * L; i += 8) out[(int64_t)t0 * L + i] = so[i];
+        __syncwarp();
+    }
+
+    // ---- backward + marginals (chunks in reverse; each thread re-reads only what its own group wrote)
+    double bt = 0.0, es_next = 0.0;
+    const int last0 = ((W - 1) / CRF_TB) * CRF_TB;
+    for (int t0 = last0; t0 >= 0; t0 -= CRF_TB) {
+        const int nt = min(CRF_TB, W - t0);
+        for (int i = y; i < nt * A; i += 8) sb[i] = __ldg(b + (int64_t)t0 * A + i);
+        for (int i = y; i < nt * L; i += 8) so[i] = out[(int64_t)t0 * L + i];
+        __syncwarp();
+        for (int tt = nt - 1; tt >= 0; tt--) {
+            const int t = t0 + tt;
+            const double cur = so[tt * L + yy];
+            const double sc = row_scale(cur);
+            if (t == W - 1) {
+                bt = sc;
+            } else {
+                const double row = GNX_MUL(bt, es_next);
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const double rk = shfl_d(row, g0 + k);
+                    if (k < L) acc = GNX_ADD(acc, GNX_MUL(etr[k], rk));
+                }
+                bt = GNX_MUL(acc, sc);
+            }
+            if (t > 0) es_next = exp_state(tt);
+            const double p = GNX_DIV(GNX_MUL(GNX_MUL(cur, sc), bt), sc);
+            __syncwarp();                                // every lane has read so[tt] before it is overwritten
+            if (y < L) so[tt * L + y] = p;
+            int best = 0;
+            double pb = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double pk = shfl_d(p, g0 + k);
+                if (k < L && (k == 0 || pk > pb)) {
+                    pb = pk;
+                    best = k;
+                }
+            }
+            if (y == 0) sl[tt] = best;
+        }
+        __syncwarp();
+        if (live) {
+            for (int i = y; i < nt * L; i += 8) out[(int64_t)t0 * L + i] = so[i];
+            if (label)
+                for (int i = y; i < nt; i += 8) label[n * W + t0 + i] = sl[i];
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace gnx
 
 struct gnx_crf {
@@ -200,6 +332,16 @@ int gnx_crf_smooth(const gnx_crf_t* m, const double* B_dev, int64_t N, int W, do
     cudaStream_t st = (cudaStream_t)stream;
     double* work = proba_dev;
     if (!work) GNX_CUDA(cudaMallocAsync((void**)&work, sizeof(double) * (size_t)N * W * m->d.L, st));
+    // lane-parallel kernel for the reference's sizes (A = L <= 8); GNX_CRF_KERNEL=0 forces the
+    // thread-per-haplotype kernel (cross-check: same bits)
+    const char* ek = getenv("GNX_CRF_KERNEL");
+    if (m->d.A <= 8 && m->d.L <= 8 && !(ek && ek[0] == '0')) {
+        crf_smooth_lanes_kernel<<<(int)ceil_div(N * 8, 128), 128, 0, st>>>(m->d, B_dev, N, W, work, label_dev);
+        cudaError_t e = cudaGetLastError();
+        if (!proba_dev) cudaFreeAsync(work, st);
+        GNX_CUDA(e);
+        return 0;
+    }
     const int grid = (int)ceil_div(N, 64);
     if (m->d.A == 7 && m->d.L == 7)
         crf_smooth_kernel<7, 7><<<grid, 64, 0, st>>>(m->d, B_dev, N, W, work, label_dev);

@@ -12,9 +12,15 @@ def _smoother(W, A, sw, tw):
     return sm
 
 
-@pytest.mark.parametrize("W,A,N", [(1430, 7, 70), (317, 7, 129), (50, 3, 10), (12, 2, 3), (200, 12, 5), (1, 7, 4)])
-def test_crf_matches_oracle(W, A, N):
+# "" = default (lane-parallel kernel for A <= 8), "0" = thread-per-haplotype kernel: same bits
+@pytest.mark.parametrize("crf_kernel", ["", "0"])
+@pytest.mark.parametrize("W,A,N", [(1430, 7, 70), (317, 7, 129), (50, 3, 10), (12, 2, 3), (200, 12, 5), (1, 7, 4), (33, 8, 37)])
+def test_crf_matches_oracle(W, A, N, crf_kernel, monkeypatch):
     from oracle import c_oracle as co
+    if crf_kernel:
+        monkeypatch.setenv("GNX_CRF_KERNEL", crf_kernel)
+    else:
+        monkeypatch.delenv("GNX_CRF_KERNEL", raising=False)
     rng = np.random.default_rng(W + A)
     sw, tw = rng.normal(0, 1.5, size=(A, A)), rng.normal(0, 1.0, size=(A, A))
     B = rng.dirichlet(np.full(A, 0.4), size=(N, W))
