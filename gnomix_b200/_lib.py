@@ -45,6 +45,7 @@ _SIGS = {
     "gnx_cal_model_create": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "gnx_cal_model_destroy": (None, [c_vp]),
     "gnx_calibrate": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp]),
+    "gnx_gnofix_last_stats": (C.c_int, [c_vp]),
     "gnx_infer_host": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64]),
     "gnx_pack_rows_host": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, C.c_int, C.POINTER(C.c_int)]),
     "gnx_unpack_dev": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),

@@ -32,8 +32,15 @@
 //     the two original haplotypes differ anywhere in that window's SNP block
 //     (gnofix_diff_kernel): X_m equals an earlier X_m iff the trackers differ only on
 //     blocks where the originals are identical.
+//   * A rejected check is remembered (one bit per window) until a switch is accepted inside its scope:
+//     the outcome of a check depends only on the current pair inside its S-window scope (and is
+//     unchanged when the whole scope sits in a swapped tail, the two candidates just trade places),
+//     and a rejected check changes no state, so skipping its repeats in later iterations is exact.
+//     Most of the reference's up-to-50 iterations re-run the same rejected checks.
 //   * A team of 256 threads owns one individual; three teams share one CTA and one copy of
 //     the forest in shared memory; teams pull individuals from a global counter.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "gbt_smooth.cuh"
@@ -53,11 +60,15 @@ struct GfArgs {
     int64_t n_ind;
     int W, nw, max_it, teams;
     size_t team_bytes;
+    unsigned long long* stats;  // [4] iterations, scans, checks, accepted switches (summed over individuals)
+    int memo;                // remember rejected checks (exact; GNX_GNOFIX_MEMO=0 re-runs them, for cross-checks)
 };
 
 __device__ __forceinline__ void team_sync(int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(GF_TEAM) : "memory");
 }
+
+static unsigned long long* g_gnofix_stats = nullptr;
 
 template <int AT>
 __global__ void __launch_bounds__(3 * GF_TEAM, 1)
@@ -79,6 +90,7 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
     const int W = g.W, S = m.S, T = m.T, ast = m.astride, nw = g.nw;
     const int pad = (S + 1) / 2, half = (S - 1) / 2;
     const int NB = 2 * S - 1;                 // staged padded slots per haplotype
+    const bool use_memo = g.memo != 0;
     const int rounds = T / A;
 
     // ---- team-private shared memory ------------------------------------------------
@@ -89,7 +101,8 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
     uint32_t* hist = reinterpret_cast<uint32_t*>(leafbuf + 4 * T);   // [max_it][nw]
     uint32_t* trk = hist + (size_t)g.max_it * nw;                    // [nw]
     uint32_t* dif = trk + nw;                                        // [nw]
-    float* marg = reinterpret_cast<float*>(dif + nw);                // [4][GBT_MAX_A]
+    uint32_t* rej = dif + nw;                                        // [nw] check at w rejected, scope unchanged since
+    float* marg = reinterpret_cast<float*>(rej + nw);                // [4][GBT_MAX_A]
     float* expv = marg + 4 * GBT_MAX_A;                              // [4][GBT_MAX_A]
     float* pmax = expv + 4 * GBT_MAX_A;                              // [4]
     int* ctl = reinterpret_cast<int*>(pmax + 4);                     // [0] next individual, [1] found w, [2] flag
@@ -105,9 +118,11 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
         for (int i = tid; i < 2 * W; i += GF_TEAM) Ys[i] = (signed char)g.Y[(size_t)(2 * ind) * W + i];
         for (int i = tid; i < nw; i += GF_TEAM) {
             trk[i] = 0u;
+            rej[i] = 0u;
             dif[i] = g.diff[(size_t)ind * nw + i];
         }
         team_sync(team);
+        unsigned long long n_it = 0, n_scan = 0, n_check = 0, n_acc = 0;
 
         for (int it = 0; it < g.max_it; it++) {
             // ---- stop if X_m was seen before (gnofix.py:108-113) ----------------------
@@ -121,6 +136,7 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
             team_sync(team);
             if (ctl[2]) break;
             for (int i = tid; i < nw; i += GF_TEAM) hist[(size_t)it * nw + i] = trk[i];
+            n_it++;
 
             int w_cur = 1;
             for (;;) {
@@ -131,13 +147,16 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
                     if (tid == 0) ctl[1] = W;
                     team_sync(team);
                     const int ww = base + tid;
-                    if (ww < W && (Ys[ww] != Ys[ww - 1] || Ys[W + ww] != Ys[W + ww - 1])) atomicMin(&ctl[1], ww);
+                    if (ww < W && (Ys[ww] != Ys[ww - 1] || Ys[W + ww] != Ys[W + ww - 1]) && !((rej[ww >> 5] >> (ww & 31)) & 1u))
+                        atomicMin(&ctl[1], ww);
                     team_sync(team);
                     w = ctl[1];
                     if (w < W) break;
                 }
+                n_scan++;
                 if (w >= W) break;
                 w_cur = w + 1;
+                n_check++;
 
                 // ---- stage padded slots [jlo, jlo + NB) of the CURRENT pair --------------
                 // rows whose receptive field straddles w (rows < pad also read reflected windows up to pad-1-row)
@@ -200,7 +219,14 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
                 }
                 team_sync(team);
                 const float p_orig = fmaxf(pmax[0], pmax[1]), p_sw = fmaxf(pmax[2], pmax[3]);
-                if (!(p_sw > p_orig)) continue;           // gnofix.py:171 (the 0.5 prior cancels)
+                if (!(p_sw > p_orig)) {                    // gnofix.py:171 (the 0.5 prior cancels)
+                    if (tid == 0 && use_memo) rej[w >> 5] |= 1u << (w & 31);
+                    continue;
+                }
+                n_acc++;
+                // a switch at w changes the pair inside every scope that contains w: forget those verdicts
+                for (int ww = max(1, w - S) + tid; ww <= min(W - 1, w + S); ww += GF_TEAM)
+                    atomicAnd(&rej[ww >> 5], ~(1u << (ww & 31)));
 
                 // ---- accept: swap tails at w --------------------------------------------
                 for (int i = tid; i < nw; i += GF_TEAM) {
@@ -227,6 +253,7 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
                 }
                 team_sync(team);
                 // rows straddling w: re-evaluate (Smoother.predict, smooth.py:58-61)
+                // (splitting the work into (row, class) tasks to balance the team was measured: no gain)
                 const int nrows = r_hi - r_lo + 1;
                 for (int task = tid; task < 2 * nrows; task += GF_TEAM) {
                     const int h = task / nrows, rr = task - h * nrows;
@@ -242,6 +269,12 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
         }
         // ---- results -----------------------------------------------------------------
         team_sync(team);
+        if (tid == 0 && g.stats) {
+            atomicAdd(g.stats + 0, n_it);
+            atomicAdd(g.stats + 1, n_scan);
+            atomicAdd(g.stats + 2, n_check);
+            atomicAdd(g.stats + 3, n_acc);
+        }
         for (int i = tid; i < 2 * W; i += GF_TEAM) g.Y[(size_t)(2 * ind) * W + i] = Ys[i];
         for (int i = tid; i < nw; i += GF_TEAM) g.trk_out[(size_t)ind * nw + i] = trk[i];
         if (g.tracker)
@@ -350,7 +383,7 @@ extern "C" int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_
         GNX_CUDA(cudaMemsetAsync(diff, 0xff, db, st));  // no X: treat every block as differing (tracker equality)
 
     const int NB = 2 * S - 1, ast = m->d.astride;
-    size_t team_bytes = (size_t)2 * NB * ast * 4 + (size_t)2 * S * ast * 4 + (size_t)4 * T * 4 + (size_t)max_it * nw * 4 + (size_t)2 * nw * 4 +
+    size_t team_bytes = (size_t)2 * NB * ast * 4 + (size_t)2 * S * ast * 4 + (size_t)4 * T * 4 + (size_t)max_it * nw * 4 + (size_t)3 * nw * 4 +
                         (size_t)(8 * GBT_MAX_A + 4) * 4 + 16 + (size_t)2 * W;
     team_bytes = (team_bytes + 15) & ~size_t(15);
     const size_t smem_max = 227 * 1024;
@@ -358,7 +391,12 @@ extern "C" int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_
     while (teams > 1 && m->rank_forest_bytes + teams * team_bytes > smem_max) teams--;
     GNX_REQUIRE(m->rank_forest_bytes + teams * team_bytes <= smem_max, "gnx_gnofix: W=%d / forest too large for shared memory", W);
     const size_t smem = m->rank_forest_bytes + teams * team_bytes;
-    GfArgs g{ranks, diff, trk, Y_dev, tracker_dev, counter, n_ind, W, nw, max_it, teams, team_bytes};
+    const char* em = getenv("GNX_GNOFIX_MEMO");
+    static unsigned long long* d_stats = nullptr;   // profiling counters of the last call on this process
+    if (!d_stats) GNX_CUDA(cudaMalloc((void**)&d_stats, 4 * sizeof(unsigned long long)));
+    GNX_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
+    g_gnofix_stats = d_stats;
+    GfArgs g{ranks, diff, trk, Y_dev, tracker_dev, counter, n_ind, W, nw, max_it, teams, team_bytes, d_stats, (em && em[0] == '0') ? 0 : 1};
     const int grid = (int)std::min<int64_t>(ceil_div(n_ind, teams), (int64_t)sm_count());
 #define CALLG(AT)                                                                                                  \
     do {                                                                                                           \
@@ -383,5 +421,17 @@ extern "C" int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_
         gnofix_apply_kernel<<<(unsigned)n_ind, 256, 0, st>>>(nullptr, 0, 0, B_dev, W, A, nw, 1, trk);
     GNX_CUDA(cudaGetLastError());
     GNX_CUDA(cudaFreeAsync(scratch, st));
+    return 0;
+}
+
+/* profiling counters of the last gnx_gnofix call of this process (synchronises the device):
+ * out[0..3] = outer iterations, discontinuity scans, candidate checks, accepted switches, summed over individuals */
+extern "C" int gnx_gnofix_last_stats(int64_t* out) {
+    GNX_REQUIRE(out != nullptr, "gnx_gnofix_last_stats: NULL");
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!gnx::g_gnofix_stats) return 0;
+    unsigned long long h[4];
+    GNX_CUDA(cudaMemcpy(h, gnx::g_gnofix_stats, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; i++) out[i] = (int64_t)h[i];
     return 0;
 }

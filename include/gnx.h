@@ -161,6 +161,11 @@ int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float*
                int64_t n_ind, int W, int max_it, int32_t* Y_dev, int32_t* tracker_dev,
                void* stream);
 
+/* profiling counters of the last gnx_gnofix call (synchronises): outer iterations, scans,
+ * candidate checks, accepted switches, summed over individuals.  GNX_GNOFIX_MEMO=0 disables
+ * the rejected-check memo (cross-check: same results). */
+int gnx_gnofix_last_stats(int64_t* out4);
+
 /* ---------------------------------------------------------------------------
  * K7  Calibrator.transform on smoother probabilities (+ argmax)
  * replaces: src/Smooth/Calibration.py:57-69 (per-class IsotonicRegression(out_of_bounds=

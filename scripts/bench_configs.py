@@ -129,6 +129,9 @@ def cfg5(N=20_000):
     torch.cuda.synchronize()
     t6 = e0.elapsed_time(e1)
     sw = (trk[0::2, 1:] != trk[0::2, :-1]).sum().item()
+    stats = np.zeros(4, dtype=np.int64)
+    lib.gnx_gnofix_last_stats(stats.ctypes.data)
+    out.update(gnofix_iterations=int(stats[0]), gnofix_scans=int(stats[1]), gnofix_checks=int(stats[2]), gnofix_accepts=int(stats[3]))
     out.update(K6_gnofix_ms=t6, gnofix_individuals_per_s=(N // 2) / (t6 * 1e-3), accepted_switches_total=int(sw),
                switches_per_individual=sw / (N // 2))
     return out

@@ -29,7 +29,13 @@ def _forest_from(d):
                      d["leaf"], d["tree_offsets"], d["base_margin"])
 
 
-def test_gnofix_matches_reference_golden():
+# "" = default (rejected checks are remembered until their scope changes), "0" = every check re-run: same results
+@pytest.mark.parametrize("memo", ["", "0"])
+def test_gnofix_matches_reference_golden(memo, monkeypatch):
+    if memo:
+        monkeypatch.setenv("GNX_GNOFIX_MEMO", memo)
+    else:
+        monkeypatch.delenv("GNX_GNOFIX_MEMO", raising=False)
     d = np.load(os.path.join(G, "gnofix.npz"))
     W, A, S, C = int(d["W"]), int(d["A"]), int(d["S"]), int(d["C"])
     model = _model(C, W, A, S, _forest_from(d))
@@ -61,8 +67,13 @@ def _planted(rng, n_ind, W, A, C, n_switch):
     return X, B
 
 
+@pytest.mark.parametrize("memo", ["", "0"])
 @pytest.mark.parametrize("W,A,S,n_ind,seed", [(160, 7, 75, 5, 0), (90, 3, 11, 12, 1), (200, 5, 25, 5, 2), (64, 2, 31, 6, 3)])
-def test_gnofix_matches_oracle(W, A, S, n_ind, seed):
+def test_gnofix_matches_oracle(W, A, S, n_ind, seed, memo, monkeypatch):
+    if memo:
+        monkeypatch.setenv("GNX_GNOFIX_MEMO", memo)
+    else:
+        monkeypatch.delenv("GNX_GNOFIX_MEMO", raising=False)
     from gnomix_b200 import GBTForest
     from oracle import c_oracle as co, np_oracle as npo
     rng = np.random.default_rng(seed)
