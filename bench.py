@@ -257,7 +257,8 @@ def run_ours(args):
     value = N * world / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through gnx_infer_host --------------------------------
-    n_e2e = min(N, args.e2e_haps)
+    # 8 ranks of one box share the host: keep the pinned e2e batch at 10 GB per rank there
+    n_e2e = min(N, args.e2e_haps if world == 1 else min(args.e2e_haps, 8192))
     Xh = torch.empty((n_e2e, ld), dtype=torch.int8, pin_memory=True)
     Xh.copy_(X[:n_e2e])
     Lh = torch.empty((n_e2e, W), dtype=torch.int32, pin_memory=True)
