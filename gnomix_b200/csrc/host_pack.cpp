@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -223,14 +224,17 @@ int host_threads_default() {
 }
 
 static Pool* g_pool = nullptr;
+static pid_t g_pool_pid = 0;
 static std::mutex g_pool_mu;
 
 static Pool* pool(int threads) {
     // workers besides the calling thread
     const int want = std::max(0, threads - 1);
+    if (g_pool && g_pool_pid != getpid()) g_pool = nullptr;  // forked child: the parent's workers do not exist here
     if (!g_pool || g_pool->size() != want) {
         delete g_pool;
         g_pool = new Pool(want);
+        g_pool_pid = getpid();
     }
     return g_pool;
 }

@@ -60,3 +60,41 @@ def test_pack_rows_threads_agree_and_empty(libgnx):
     # bad arguments: pitch too small
     o = np.zeros(4, dtype=np.uint64)
     assert libgnx.gnx_pack_rows_host(X.ctypes.data, 1, cols, cols, o.ctypes.data, 4, 1, None) != 0
+
+
+def test_host_threads_env(libgnx, monkeypatch):
+    """GNX_HOST_THREADS pins the count; under torchrun the ranks of a node split the cores."""
+    monkeypatch.delenv("GNX_HOST_THREADS", raising=False)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    n = libgnx.gnx_host_threads()
+    assert 1 <= n <= 128
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "4")
+    assert libgnx.gnx_host_threads() == max(1, n // 4)
+    monkeypatch.setenv("GNX_HOST_THREADS", "3")
+    assert libgnx.gnx_host_threads() == 3
+
+
+def test_pack_after_fork(libgnx):
+    """The worker pool is rebuilt in a forked child instead of waiting for threads that only exist in the parent."""
+    rng = np.random.default_rng(6)
+    X = rng.integers(0, 3, size=(64, 70_001), dtype=np.int8)
+    ref, _ = _pack(libgnx, X, 70_001, threads=4)          # creates the pool in this process
+    pid = os.fork()
+    if pid == 0:
+        ok = 1
+        try:
+            out, bad = _pack(libgnx, X, 70_001, threads=4)
+            ok = 0 if (bad == 0 and np.array_equal(out, ref)) else 2
+        finally:
+            os._exit(ok)
+    import time
+    for _ in range(200):
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            break
+        time.sleep(0.05)
+    else:
+        os.kill(pid, 9)
+        os.waitpid(pid, 0)
+        raise AssertionError("forked child hung in gnx_pack_rows_host")
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
