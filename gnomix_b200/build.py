@@ -67,7 +67,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         if verbose and out:
             print(out)
     tmp = LIB + ".tmp"
-    cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-lpthread"]
+    cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-lpthread", "-lz"]
     subprocess.check_call(cmd, env=env)
     os.replace(tmp, LIB)
     return LIB

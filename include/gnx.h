@@ -37,6 +37,7 @@ typedef struct gnx_gbt gnx_gbt_t; /* gradient-boosted-tree smoother (K4)      */
 typedef struct gnx_crf gnx_crf_t; /* linear-chain CRF smoother (K5)           */
 typedef struct gnx_svc gnx_svc_t; /* CovRSK string-kernel SVC base (K2+K3)    */
 typedef struct gnx_cal gnx_cal_t; /* per-class isotonic calibrator (K7)        */
+typedef struct gnx_vcf gnx_vcf_t; /* parsed VCF (host side)                    */
 
 int gnx_version(void);
 const char* gnx_last_error(void);
@@ -232,6 +233,24 @@ int gnx_infer_host_last_transfer(double* frac, int64_t* h2d_bytes, int64_t* d2h_
 int gnx_write_fb_body(const char* path, int append, const void* proba, int is_f64, int64_t N,
                       int64_t W, int64_t A, const char* const* prefixes, int threads);
 int64_t gnx_format_floats(const void* values, int is_f64, int64_t n, char* out, int64_t cap);
+/* ---------------------------------------------------------------------------
+ * Host-side input of run_inference: VCF(.gz) -> genotype calls
+ * replaces: allel.read_vcf behind read_vcf (src/utils.py:55-81) for the fields the reference
+ *           reads (calldata/GT, variants/POS|REF|ALT|CHROM|ID|QUAL, samples).
+ * gnx_vcf_open inflates the file (plain / gzip / bgzip), keeps the records whose CHROM equals
+ * `chm` (NULL: all) and parses them on `threads` host threads (<= 0: gnx_host_threads()).
+ * gnx_vcf_copy: gt [records][samples][2] int8 (-1 = missing or haploid second allele),
+ * pos [records] int32, qual [records] float32 (NaN for '.'); any pointer may be NULL.
+ * gnx_vcf_strings: field 0 CHROM, 1 ID, 2 REF, 3 ALT (comma-separated as in the file),
+ * 4 sample names; every string followed by a newline is written into buf when cap suffices;
+ * returns the bytes needed (call with buf = NULL first).
+ * ------------------------------------------------------------------------- */
+int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads);
+void gnx_vcf_close(gnx_vcf_t* v);
+int64_t gnx_vcf_num_records(const gnx_vcf_t* v);
+int64_t gnx_vcf_num_samples(const gnx_vcf_t* v);
+int gnx_vcf_copy(const gnx_vcf_t* v, int8_t* gt, int32_t* pos, float* qual);
+int64_t gnx_vcf_strings(const gnx_vcf_t* v, int field, char* buf, int64_t cap);
 /* host threads the library uses (cores this process may run on, or GNX_HOST_THREADS) */
 int gnx_host_threads(void);
 

@@ -142,3 +142,60 @@ def test_write_fb_native_body_matches_numpy_formatting(tmp_path):
         out = C.create_string_buffer(a.size * 34 + 8)
         n = _lib.lib().gnx_format_floats(a.ctypes.data, int(dt == np.float64), a.size, out, len(out))
         assert out.raw[:n].decode().split("\n")[:-1] == list(a.astype(str))
+
+
+def _same_vcf(a, b):
+    assert set(a) == set(b)
+    for k in b:
+        if a[k].dtype == np.float32:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+        else:
+            assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+
+
+def test_native_vcf_reader_matches_python_parser(tmp_path):
+    """gnx_vcf_open (csrc/host_vcf.cpp) against the pure-Python restatement of allel.read_vcf's fields
+    (src/utils.py:55-81) on awkward records: missing and haploid calls, unphased separators, extra FORMAT
+    keys, multi-allelic ALT, multi-digit alleles, CRLF, a short line, two chromosomes, no final newline, gzip."""
+    from gnomix_b200 import io as gio
+    hdr = "##fileformat=VCFv4.2\n##contig=<ID=7>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\tS3\n"
+    rows = [
+        "7\t100\trs1\tA\tG\t.\tPASS\t.\tGT\t0|1\t1|1\t0|0",
+        "7\t150\t.\tC\tT,G\t30.5\tq10\tDP=4\tGT:DP\t1/0:3\t.|.:0\t2|1:9",
+        "7\t160\trs3\tG\tA,C,T,GG\t7\t.\t.\tGT\t0\t.\t1",
+        "8\t170\trs4\tT\tC\t.\t.\t.\tGT\t1|1\t1|1\t1|1",
+        "7\t180\tshort\tA\tC",
+        "7\t190\trs5\tT\tC\t99\t.\t.\tGT:GQ\t10|0:1\t0|.\t./1:5",
+        "7\t200\trs6\tAT\tA\t.\t.\t.\tGT\t0|0\t0|1",
+    ]
+    plain = tmp_path / "a.vcf"
+    plain.write_text(hdr + "\n".join(rows))                       # no final newline
+    crlf = tmp_path / "b.vcf"
+    crlf.write_bytes((hdr + "\n".join(rows) + "\n").replace("\n", "\r\n").encode())
+    gz = tmp_path / "c.vcf.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write((hdr + "\n".join(rows) + "\n").encode())
+    for path in (plain, gz):
+        for chm in ("7", "8", None, "9"):
+            _same_vcf(gio.read_vcf(str(path), chm), gio.read_vcf_py(str(path), chm))
+    d = gio.read_vcf(str(plain), "7")
+    assert d["calldata/GT"].shape == (5, 3, 2) and list(d["variants/POS"]) == [100, 150, 160, 190, 200]
+    assert d["calldata/GT"][1].tolist() == [[1, 0], [-1, -1], [2, 1]] and d["calldata/GT"][2].tolist() == [[0, -1], [-1, -1], [1, -1]]
+    assert d["calldata/GT"][3].tolist() == [[10, 0], [0, -1], [-1, 1]] and d["calldata/GT"][4].tolist() == [[0, 0], [0, 1], [-1, -1]]
+    assert list(d["variants/ALT"][2]) == ["A", "C", "T"] and list(d["samples"]) == ["S1", "S2", "S3"]
+    c = gio.read_vcf(str(crlf), "7")
+    assert np.array_equal(c["calldata/GT"], d["calldata/GT"]) and list(c["samples"]) == ["S1", "S2", "S3"]
+    # a larger random cohort, threads or not
+    rng = np.random.default_rng(2)
+    lut = np.array(["0|0", "0|1", "1|0", "1|1", ".|.", "0/1"])
+    big = tmp_path / "big.vcf.gz"
+    with gzip.open(big, "wt") as f:
+        f.write(hdr.replace("S1\tS2\tS3", "\t".join("X%d" % i for i in range(40))))
+        for r in range(6000):
+            f.write("7\t%d\tr%d\tA\tG\t.\t.\t.\tGT\t%s\n" % (10 + 3 * r, r, "\t".join(lut[rng.integers(0, 6, 40)])))
+    for th in ("1", "5"):
+        os.environ["GNX_HOST_THREADS"] = th
+        _same_vcf(gio.read_vcf(str(big), "7"), gio.read_vcf_py(str(big), "7"))
+    os.environ.pop("GNX_HOST_THREADS", None)
+    with pytest.raises(Exception):
+        gio.read_vcf(str(tmp_path / "missing.vcf"))
