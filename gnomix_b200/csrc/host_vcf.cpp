@@ -321,4 +321,40 @@ int64_t gnx_vcf_strings(const gnx_vcf_t* v, int field, char* buf, int64_t cap) {
     return need;
 }
 
+
+/* Genotype block -> aligned haplotype matrix (reference src/utils.py:104-159, vcf_to_npy after the SNP
+ * intersection): X[2s + h][fmt_idx[k]] = GT[vcf_idx[k]][s][h] for k < n_idx, flipped 0 <-> 1 where
+ * swap[k] (reference alleles disagree), everything that is not 0 / 1 and every column outside fmt_idx
+ * = miss_fill.  gt [R][S][2] int8, X [2S][ldX] int8 (C columns written).  Parallel over blocks of 64
+ * haplotype rows: each record contributes one 64-byte read per block. */
+int gnx_vcf_to_haplotypes(const int8_t* gt, int64_t R, int64_t S, const int64_t* vcf_idx, const int64_t* fmt_idx,
+                          const uint8_t* swap, int64_t n_idx, int64_t C, int miss_fill, int8_t* X, int64_t ldX, int threads) {
+    if (R < 0 || S < 0 || n_idx < 0 || C < 0 || ldX < C || (n_idx > 0 && (!gt || !vcf_idx || !fmt_idx)) || (2 * S * C > 0 && !X)) {
+        gnx::set_error("gnx_vcf_to_haplotypes: bad arguments");
+        return 2;
+    }
+    for (int64_t k = 0; k < n_idx; k++)
+        if (vcf_idx[k] < 0 || vcf_idx[k] >= R || fmt_idx[k] < 0 || fmt_idx[k] >= C) {
+            gnx::set_error("gnx_vcf_to_haplotypes: index %lld out of range", (long long)k);
+            return 2;
+        }
+    const int64_t H = 2 * S;
+    const int64_t nblk = (H + 63) / 64;
+    const int8_t mf = (int8_t)miss_fill;
+    gnx::parallel_for(nblk, threads, [&](int64_t b) {
+        const int64_t h0 = b * 64, hn = std::min<int64_t>(64, H - h0);
+        for (int64_t h = 0; h < hn; h++) memset(X + (h0 + h) * ldX, mf, (size_t)C);
+        for (int64_t k = 0; k < n_idx; k++) {
+            const int8_t* src = gt + vcf_idx[k] * H + h0;
+            int8_t* dst = X + h0 * ldX + fmt_idx[k];
+            const bool sw = swap && swap[k];
+            for (int64_t h = 0; h < hn; h++) {
+                const int8_t v = src[h];
+                dst[h * ldX] = (v == 0 || v == 1) ? (int8_t)(sw ? 1 - v : v) : mf;
+            }
+        }
+    });
+    return 0;
+}
+
 }  // extern "C"

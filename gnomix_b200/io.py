@@ -157,7 +157,39 @@ def snp_intersection(pos1, pos2, verbose=False):
 def vcf_to_npy(vcf_data, snp_pos_fmt=None, snp_ref_fmt=None, miss_fill=2, return_idx=False, verbose=True):
     """src/utils.py:104-159: align to the model's SNP positions (missing positions = miss_fill),
     flip 0/1 where the reference alleles disagree, anything that is not 0/1 -> miss_fill; int8
-    [2 * individuals, C] with rows 2i, 2i+1 = individual i."""
+    [2 * individuals, C] with rows 2i, 2i+1 = individual i.  The transposing gather runs on the
+    library's host threads (gnx_vcf_to_haplotypes); vcf_to_npy_py is the numpy statement of it."""
+    from . import _lib
+    gt = vcf_data["calldata/GT"]
+    if not (isinstance(gt, np.ndarray) and gt.dtype == np.int8 and gt.ndim == 3 and gt.shape[2] == 2):
+        return vcf_to_npy_py(vcf_data, snp_pos_fmt, snp_ref_fmt, miss_fill, return_idx, verbose)
+    gt = np.ascontiguousarray(gt)
+    R, S, _ = gt.shape
+    if snp_pos_fmt is not None:
+        fmt_idx, vcf_idx = snp_intersection(snp_pos_fmt, vcf_data["variants/POS"], verbose=verbose)
+        C = len(snp_pos_fmt)
+    else:
+        fmt_idx = vcf_idx = np.arange(R)
+        C = R
+    swap = None
+    if snp_ref_fmt is not None:
+        swap = np.asarray(vcf_data["variants/REF"])[vcf_idx] != np.asarray(snp_ref_fmt)[fmt_idx]
+        if swap.any() and verbose:
+            print("- Found ", int(swap.sum()), " (", round(np.mean(swap) * 100, 4), "%) different reference variants. Adjusting...", sep="")
+        swap = np.ascontiguousarray(swap, dtype=np.uint8)
+    vi = np.ascontiguousarray(vcf_idx, dtype=np.int64)
+    fi = np.ascontiguousarray(fmt_idx, dtype=np.int64)
+    mat = np.empty((2 * S, C), dtype=np.int8)
+    _lib.check(_lib.lib().gnx_vcf_to_haplotypes(gt.ctypes.data, R, S, vi.ctypes.data, fi.ctypes.data,
+                                                None if swap is None else swap.ctypes.data, len(vi), C, int(miss_fill),
+                                                mat.ctypes.data, C, 0), "gnx_vcf_to_haplotypes")
+    if return_idx:
+        return mat, (vcf_idx if snp_pos_fmt is not None else np.arange(2 * S)), (fmt_idx if snp_pos_fmt is not None else np.arange(2 * S))
+    return mat
+
+
+def vcf_to_npy_py(vcf_data, snp_pos_fmt=None, snp_ref_fmt=None, miss_fill=2, return_idx=False, verbose=True):
+    """src/utils.py:104-159 in numpy, statement by statement."""
     data = vcf_data["calldata/GT"]
     chm_len, n_ind, _ = data.shape
     data = data.reshape(chm_len, n_ind * 2).T

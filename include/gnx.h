@@ -251,6 +251,12 @@ int64_t gnx_vcf_num_records(const gnx_vcf_t* v);
 int64_t gnx_vcf_num_samples(const gnx_vcf_t* v);
 int gnx_vcf_copy(const gnx_vcf_t* v, int8_t* gt, int32_t* pos, float* qual);
 int64_t gnx_vcf_strings(const gnx_vcf_t* v, int field, char* buf, int64_t cap);
+/* vcf_to_npy after the SNP intersection (src/utils.py:121-153): X[2s+h][fmt_idx[k]] =
+ * gt[vcf_idx[k]][s][h], flipped 0 <-> 1 where swap[k] (nullable), everything that is not 0 / 1 and
+ * every column outside fmt_idx = miss_fill.  gt [R][S][2] int8, X [2S][ldX] int8 host memory. */
+int gnx_vcf_to_haplotypes(const int8_t* gt, int64_t R, int64_t S, const int64_t* vcf_idx,
+                          const int64_t* fmt_idx, const uint8_t* swap, int64_t n_idx, int64_t C,
+                          int miss_fill, int8_t* X, int64_t ldX, int threads);
 /* host threads the library uses (cores this process may run on, or GNX_HOST_THREADS) */
 int gnx_host_threads(void);
 

@@ -199,3 +199,27 @@ def test_native_vcf_reader_matches_python_parser(tmp_path):
     os.environ.pop("GNX_HOST_THREADS", None)
     with pytest.raises(Exception):
         gio.read_vcf(str(tmp_path / "missing.vcf"))
+
+
+def test_native_vcf_to_npy_matches_numpy_statement():
+    """gnx_vcf_to_haplotypes against vcf_to_npy_py (src/utils.py:104-159 statement by statement): SNP intersection,
+    reference-allele flips, missing / multi-allelic calls -> miss_fill, with and without a model format."""
+    from gnomix_b200 import io as gio
+    rng = np.random.default_rng(12)
+    for R, S in [(1, 1), (300, 3), (2000, 70), (777, 33)]:
+        gt = rng.integers(-1, 4, (R, S, 2), dtype=np.int8)
+        pos = np.sort(rng.choice(np.arange(10, 50 * R + 100), R, replace=False)).astype(np.int32)
+        ref = rng.choice(np.array(["A", "C", "G", "T"], dtype=object), R)
+        d = {"calldata/GT": gt, "variants/POS": pos, "variants/REF": ref}
+        keep = np.sort(rng.choice(R, max(1, R * 3 // 4), replace=False))
+        extra = np.setdiff1d(rng.choice(np.arange(10, 50 * R + 100), max(1, R // 5)), pos)
+        mp = np.sort(np.concatenate([pos[keep], extra]))
+        mr = rng.choice(np.array(["A", "C", "G", "T"], dtype=object), len(mp))
+        for fill in (2, 9):
+            a = gio.vcf_to_npy(d, mp, mr, miss_fill=fill, verbose=False)
+            b = gio.vcf_to_npy_py({k: (v.copy() if hasattr(v, "copy") else v) for k, v in d.items()}, mp, mr, miss_fill=fill, verbose=False)
+            assert a.dtype == np.int8 and np.array_equal(a, b), (R, S, fill)
+        a, vi, fi = gio.vcf_to_npy(d, mp, None, return_idx=True, verbose=False)
+        b, vj, fj = gio.vcf_to_npy_py(d, mp, None, return_idx=True, verbose=False)
+        assert np.array_equal(a, b) and np.array_equal(vi, vj) and np.array_equal(fi, fj)
+        assert np.array_equal(gio.vcf_to_npy(d, verbose=False), gio.vcf_to_npy_py(d, verbose=False))
