@@ -118,6 +118,12 @@ def run_inference(base_args, model, snp_level=False, bed_file_output=False, verb
     out_prefix = output_path + "/" + "query_results"
     pp.write_msp(out_prefix, meta, y_pred, model.population_order, vcf["samples"])
     pp.write_fb(out_prefix, meta, y_proba, model.population_order, vcf["samples"])
+    if snp_level:                                   # gnomix.py:83-84 (BETA)
+        pp.msp_to_lai(msp_file=out_prefix + ".msp", positions=vcf["variants/POS"], lai_file=out_prefix + ".lai")
+    if bed_file_output:                             # gnomix.py:86-90
+        bed_root = output_path + "/" + "query_results_bed"
+        os.makedirs(bed_root, exist_ok=True)
+        pp.msp_to_bed(msp_file=out_prefix + ".msp", root=bed_root, pop_order=model.population_order)
     return out_prefix
 
 

@@ -114,3 +114,65 @@ def write_fb(fb_prefix, meta_data, proba, ancestry, query_samples):
     arr = (C.c_char_p * n_rows)(*prefixes)
     _lib.check(_lib.lib().gnx_write_fb_body(path.encode(), 1, proba.ctypes.data, int(proba.dtype == np.float64), N, W, A,
                                             C.cast(arr, C.c_void_p), 0), "gnx_write_fb_body")
+
+
+def msp_to_lai(msp_file, positions, lai_file=None):
+    """src/postprocess.py:128-160 (BETA in the reference): per-SNP ancestry by repeating every window's row
+    `n snps` times; same DataFrame and, with lai_file, the same file."""
+    import pandas as pd
+    positions = np.asarray(positions)
+    msp_df = pd.read_csv(msp_file, sep="\t", comment="#", header=None)
+    data_window = np.array(msp_df.iloc[:, 6:])
+    n_reps = msp_df.iloc[:, 5].to_numpy()
+    assert np.sum(n_reps) == len(positions)
+    data_snp = np.repeat(data_window, n_reps, axis=0)
+    pos_lower_bound = int(msp_df.iloc[0, 1])
+    pos_upper_bound = int(msp_df.iloc[-1, 2])
+    extrapolating_lo = np.sum(positions < pos_lower_bound)
+    extrapolating_hi = np.sum(positions > pos_upper_bound)
+    if extrapolating_lo > 0:
+        print("WARNING: Extrapolating ancestry inference for {} SNPs (lower bound is position {})".format(extrapolating_lo, pos_lower_bound))
+    if extrapolating_hi > 0:
+        print("WARNING: Extrapolating ancestry inference for {} SNPs (upper bound is position {})".format(extrapolating_hi, pos_upper_bound))
+    with open(msp_file) as f:
+        first_line = f.readline()
+        second_line = f.readline()
+    samples = second_line[:-1].split("\t")[6:]
+    df = pd.DataFrame(data_snp, columns=samples, index=positions)
+    if lai_file is not None:
+        with open(lai_file, "w") as f:
+            f.write(first_line)
+        df.to_csv(lai_file, sep="\t", mode="a", index_label="position")
+    return df
+
+
+def get_bed_data(msp_df, sample, pop_order=None):
+    """src/postprocess.py:162-193: one row per maximal run of equal ancestry (change points found at once
+    instead of a Python loop over windows)."""
+    anc = np.asarray(msp_df[sample])
+    start = np.concatenate([[0], np.flatnonzero(anc[1:] != anc[:-1]) + 1])
+    stop = np.concatenate([start[1:] - 1, [len(anc) - 1]])
+    label = (lambda v: v) if pop_order is None else (lambda v: pop_order[v])
+    return {
+        "chm": np.asarray(msp_df["#chm"])[start].astype(int),
+        "spos": np.asarray(msp_df["spos"])[start].astype(int),
+        "epos": np.asarray(msp_df["epos"])[stop].astype(int),
+        "ancestry": [label(v) for v in anc[start]],
+        "sgpos": list(np.asarray(msp_df["sgpos"])[start]),
+        "egpos": list(np.asarray(msp_df["egpos"])[stop]),
+    }
+
+
+def msp_to_bed(msp_file, root, pop_order=None):
+    """src/postprocess.py:195-210: one .bed per haplotype column.  Like the reference, the header line is
+    split without stripping its newline, so the last haplotype's file name ends in "\\n.bed"."""
+    import os
+    import pandas as pd
+    with open(msp_file) as f:
+        _ = f.readline()
+        second_line = f.readline()
+    header = second_line.split("\t")
+    msp_df = pd.read_csv(msp_file, sep="\t", comment="#", names=header)
+    for sample in header[6:]:
+        sample_file_name = os.path.join(root, sample.replace(".", "_") + ".bed")
+        pd.DataFrame(get_bed_data(msp_df, sample, pop_order=pop_order)).to_csv(sample_file_name, sep="\t", index=False)

@@ -22,6 +22,7 @@ What each file pins (reference file:line):
                     (src/Smooth/smooth.py:40-65) driven with the oracle's tree predictor as
                     smoother.model (xgboost itself is not installable here).
   meta.npz          get_meta_data (src/postprocess.py:25-67).
+  lai_bed.npz       msp_to_lai / msp_to_bed (src/postprocess.py:128-210) on the .msp of meta.npz.
   calibrator.npz    Calibrator.fit / transform (src/Smooth/Calibration.py:19-69) through
                     scikit-learn IsotonicRegression.
 """
@@ -280,6 +281,30 @@ def golden_vcf_to_npy(src):
     print("vcf_to_npy", X.shape, X.dtype, np.bincount(X.ravel()))
 
 
+def golden_lai_bed(src):
+    """msp_to_lai + msp_to_bed (src/postprocess.py:128-210) on the .msp of meta.npz; the written
+    files are stored byte for byte."""
+    import tempfile
+    from src.postprocess import msp_to_lai, msp_to_bed
+    d = np.load(os.path.join(OUT, "meta.npz"))
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        msp = os.path.join(td, "q.msp")
+        open(msp, "wb").write(d["msp"].tobytes())
+        msp_to_lai(msp_file=msp, positions=d["qpos"], lai_file=os.path.join(td, "q.lai"))
+        out["lai"] = np.frombuffer(open(os.path.join(td, "q.lai"), "rb").read(), dtype=np.uint8)
+        for tag, pop_order in (("num", None), ("pop", d["pops"].tolist())):
+            root = os.path.join(td, "bed_" + tag)
+            os.makedirs(root)
+            msp_to_bed(msp_file=msp, root=root, pop_order=pop_order)
+            names = sorted(os.listdir(root))
+            out["bed_%s_names" % tag] = np.array(names)
+            for i, nm in enumerate(names):
+                out["bed_%s_%d" % (tag, i)] = np.frombuffer(open(os.path.join(root, nm), "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "lai_bed.npz"), **out)
+    print("lai_bed", len(out["lai"]), list(out["bed_num_names"]))
+
+
 def golden_calibrator(src):
     """Calibrator.fit / transform (src/Smooth/Calibration.py:19-69) with scikit-learn's
     IsotonicRegression: float32 probabilities (what the XGB smoother returns), float64
@@ -330,6 +355,7 @@ def main():
     golden_meta(src)
     golden_vcf_to_npy(src)
     golden_calibrator(src)
+    golden_lai_bed(src)
 
 
 if __name__ == "__main__":

@@ -223,3 +223,24 @@ def test_native_vcf_to_npy_matches_numpy_statement():
         b, vj, fj = gio.vcf_to_npy_py(d, mp, None, return_idx=True, verbose=False)
         assert np.array_equal(a, b) and np.array_equal(vi, vj) and np.array_equal(fi, fj)
         assert np.array_equal(gio.vcf_to_npy(d, verbose=False), gio.vcf_to_npy_py(d, verbose=False))
+
+
+def test_lai_and_bed_outputs_byte_identical(tmp_path):
+    """msp_to_lai / msp_to_bed against files written by the reference's own functions (src/postprocess.py:128-210,
+    tests/golden/lai_bed.npz) from the .msp of meta.npz -- including the reference's "\\n.bed" name of the last column."""
+    from gnomix_b200 import postprocess as pp
+    d = np.load(os.path.join(G, "meta.npz"))
+    g = np.load(os.path.join(G, "lai_bed.npz"))
+    msp = tmp_path / "q.msp"
+    msp.write_bytes(d["msp"].tobytes())
+    df = pp.msp_to_lai(str(msp), d["qpos"], lai_file=str(tmp_path / "q.lai"))
+    assert df.shape == (len(d["qpos"]), d["labels"].shape[0])
+    assert open(tmp_path / "q.lai", "rb").read() == g["lai"].tobytes()
+    for tag, pop_order in (("num", None), ("pop", d["pops"].tolist())):
+        root = tmp_path / ("bed_" + tag)
+        root.mkdir()
+        pp.msp_to_bed(str(msp), str(root), pop_order=pop_order)
+        names = sorted(os.listdir(root))
+        assert names == g["bed_%s_names" % tag].tolist()
+        for i, nm in enumerate(names):
+            assert open(root / nm, "rb").read() == g["bed_%s_%d" % (tag, i)].tobytes(), (tag, nm)
