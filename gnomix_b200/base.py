@@ -34,7 +34,12 @@ def to_device_haplotypes(X):
     N, Cc = src.shape
     ld = (Cc + 127) // 128 * 128
     buf = torch.empty((N, ld), dtype=torch.int8, device="cuda")
-    buf[:, :Cc].copy_(src.view(torch.int8) if src.dtype == torch.uint8 else src, non_blocking=False)
+    if not src.is_cuda and N > 0 and src.stride(1) == 1:
+        # host matrix: packed transfer (2 bits per SNP over PCIe, gnx_upload_haplotypes)
+        torch.cuda.current_stream().synchronize()
+        _lib.check(_lib.lib().gnx_upload_haplotypes(src.data_ptr(), N, src.stride(0), Cc, buf.data_ptr(), ld), "gnx_upload_haplotypes")
+    else:
+        buf[:, :Cc].copy_(src.view(torch.int8) if src.dtype == torch.uint8 else src, non_blocking=False)
     return buf[:, :Cc], ld
 
 

@@ -96,12 +96,12 @@ static int ensure(Workspace& ws, size_t xb, size_t bb, size_t pb, size_t lb, siz
         lb = std::max(lb, ws.l_bytes); pkb = std::max(pkb, ws.pk_bytes);
         ws.release();
         for (int i = 0; i < 2; i++) {
-            GNX_CUDA(cudaMalloc((void**)&ws.X[i], xb));
-            GNX_CUDA(cudaMalloc((void**)&ws.B[i], bb));
+            if (xb) GNX_CUDA(cudaMalloc((void**)&ws.X[i], xb));
+            if (bb) GNX_CUDA(cudaMalloc((void**)&ws.B[i], bb));
             if (pb) GNX_CUDA(cudaMalloc((void**)&ws.P[i], pb));
             if (pb) GNX_CUDA(cudaHostAlloc((void**)&ws.Ph[i], pb, cudaHostAllocDefault));
-            GNX_CUDA(cudaMalloc((void**)&ws.Lb[i], lb));
-            GNX_CUDA(cudaHostAlloc((void**)&ws.Lh[i], lb, cudaHostAllocDefault));
+            if (lb) GNX_CUDA(cudaMalloc((void**)&ws.Lb[i], lb));
+            if (lb) GNX_CUDA(cudaHostAlloc((void**)&ws.Lh[i], lb, cudaHostAllocDefault));
             if (pkb) GNX_CUDA(cudaMalloc((void**)&ws.PK[i], pkb));
         }
         if (pkb)
@@ -309,5 +309,67 @@ extern "C" int gnx_infer_host_last_transfer(double* frac, int64_t* h2d_bytes, in
     if (frac) *frac = g_ws.last_frac;
     if (h2d_bytes) *h2d_bytes = g_ws.last_h2d;
     if (d2h_bytes) *d2h_bytes = g_ws.last_d2h;
+    return 0;
+}
+
+/* Host int8 matrix -> device int8 matrix [N, ld_dev] (ld_dev a multiple of 128 >= C, the pitch K1 / K2 address),
+ * through the same packed transfer as gnx_infer_host: the cores pack chunk i+1 to 2-bit planes while chunk i
+ * crosses the bus, unpack_kernel restores the bytes in place.  Pinned input splits every chunk between packed
+ * and raw rows like gnx_infer_host; chunks with values outside 0..3 go raw.  Synchronous. */
+extern "C" int gnx_upload_haplotypes(const int8_t* X_host, int64_t N, int64_t ldX, int64_t C, int8_t* X_dev, int64_t ld_dev) {
+    GNX_REQUIRE(N >= 0 && C >= 1 && ldX >= C, "gnx_upload_haplotypes: bad shape");
+    GNX_REQUIRE(ld_dev % 128 == 0 && ld_dev >= C && ((uintptr_t)X_dev & 15) == 0, "gnx_upload_haplotypes: ld_dev must be a multiple of 128 >= C and X_dev 16-byte aligned");
+    if (N == 0) return 0;
+    GNX_REQUIRE(X_host && X_dev, "gnx_upload_haplotypes: NULL buffer");
+    if (require_blackwell()) return 1;
+    const int64_t pitch = (C + 127) & ~int64_t(127);
+    const int64_t pitch_words = pitch / 32;
+    if (!env_pack_enabled()) {
+        GNX_CUDA(cudaMemcpy2D(X_dev, (size_t)ld_dev, X_host, (size_t)ldX, (size_t)C, (size_t)N, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int64_t chunk = std::max<int64_t>(256, (int64_t(5) << 27) / pitch / 256 * 256);
+    chunk = std::min<int64_t>(chunk, (N + 255) / 256 * 256);
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    Workspace& ws = g_ws;
+    if (ensure(ws, 0, 0, 0, 0, (size_t)chunk * pitch_words * 8)) return 1;
+    const int threads = host_threads_default();
+    double frac = 1.0;
+    const char* fe = getenv("GNX_HOST_PACK_FRAC");
+    if (fe && *fe) {
+        frac = std::min(1.0, std::max(0.0, atof(fe)));
+    } else if (is_pinned(X_host)) {
+        if (ws.pack_gbs <= 0.0 || ws.calib_threads != threads) {
+            if (calibrate(ws, X_host, N, ldX, C, pitch_words, threads)) return 1;
+            ws.frac_hint = 0.0;
+        }
+        if (ws.pack_gbs > 0.0 && ws.h2d_gbs > 0.0)
+            frac = ws.frac_hint > 0.0 ? ws.frac_hint : 1.0 / (ws.h2d_gbs / (0.85 * ws.pack_gbs) + 0.75);
+    }
+    bool stage_used[kStage] = {};
+    int it = 0;
+    for (int64_t n0 = 0; n0 < N; n0 += chunk, it++) {
+        const int s = it & 1, hs = it % kStage;
+        const int64_t n = std::min(chunk, N - n0);
+        cudaStream_t st = ws.st[s];
+        int8_t* dst = X_dev + n0 * ld_dev;
+        const int64_t np = frac >= 1.0 ? n : (int64_t)(frac * (double)n);
+        if (np < n)
+            GNX_CUDA(cudaMemcpy2DAsync(dst + np * ld_dev, (size_t)ld_dev, X_host + (n0 + np) * ldX, (size_t)ldX, (size_t)C,
+                                       (size_t)(n - np), cudaMemcpyHostToDevice, st));
+        if (np == 0) continue;
+        if (stage_used[hs]) GNX_CUDA(cudaEventSynchronize(ws.h2d_done[hs]));
+        if (pack_rows(X_host + n0 * ldX, np, ldX, C, ws.stage[hs], pitch_words, threads, nullptr) == 0) {
+            GNX_CUDA(cudaMemcpyAsync(ws.PK[s], ws.stage[hs], (size_t)np * pitch_words * 8, cudaMemcpyHostToDevice, st));
+            GNX_CUDA(cudaEventRecord(ws.h2d_done[hs], st));
+            stage_used[hs] = true;
+            if (unpack_rows(ws.PK[s], np, pitch_words, C, dst, ld_dev, st)) return 1;
+        } else {
+            GNX_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld_dev, X_host + n0 * ldX, (size_t)ldX, (size_t)C, (size_t)np,
+                                       cudaMemcpyHostToDevice, st));
+        }
+    }
+    GNX_CUDA(cudaStreamSynchronize(ws.st[0]));
+    GNX_CUDA(cudaStreamSynchronize(ws.st[1]));
     return 0;
 }

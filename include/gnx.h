@@ -215,6 +215,11 @@ int gnx_pack_rows_host(const int8_t* X_host, int64_t n, int64_t ldX, int64_t C, 
                        int64_t pitch_words, int threads, int* out_of_range);
 int gnx_unpack_dev(const uint64_t* packed_dev, int64_t n, int64_t pitch_words, int64_t C,
                    int8_t* X_dev, int64_t ldX, void* stream);
+/* Host int8 matrix [N, ldX] -> device int8 matrix [N, ld_dev] (ld_dev a multiple of 128 >= C,
+ * the row pitch the base kernels address) through the same packed transfer; synchronous.
+ * This is how the Python plugins upload a numpy haplotype matrix (Base.predict_proba, phase). */
+int gnx_upload_haplotypes(const int8_t* X_host, int64_t N, int64_t ldX, int64_t C, int8_t* X_dev,
+                          int64_t ld_dev);
 /* rates measured by gnx_infer_host's one-off calibration (0 before it ran): host pack
  * rate in GB/s of int8 input, pinned H2D rate in GB/s */
 int gnx_infer_host_rates(double* pack_gbs, double* h2d_gbs);

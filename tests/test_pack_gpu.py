@@ -78,3 +78,34 @@ def test_infer_host_same_results_for_every_packed_fraction(pinned, monkeypatch):
         from gnomix_b200 import _lib
         _lib.lib().gnx_infer_host_rates(C.byref(pk), C.byref(h2d))
         assert pk.value > 0 and h2d.value > 0
+
+
+def test_upload_haplotypes_equals_plain_copy(libgnx, monkeypatch):
+    """gnx_upload_haplotypes (what Base.predict_proba uses for a numpy matrix): the device matrix equals the host
+    matrix for pageable / pinned input, ragged shapes, strided rows, unpackable values, packing on or off."""
+    import torch
+    from gnomix_b200 import _lib
+    from gnomix_b200.base import to_device_haplotypes
+    _lib.require_gpu()
+    rng = np.random.default_rng(31)
+    for N, Cc in [(1, 1), (5, 127), (300, 129), (1000, 40_013), (2600, 9_001)]:
+        X = rng.integers(0, 3, size=(N, Cc + 5), dtype=np.int8)[:, :Cc]      # row stride != C
+        X = np.ascontiguousarray(X) if N == 5 else X
+        for pinned in (False, True):
+            src = torch.from_numpy(np.ascontiguousarray(X)).pin_memory() if pinned else X
+            for frac in (None, "0.4", "0"):
+                if frac is None:
+                    monkeypatch.delenv("GNX_HOST_PACK_FRAC", raising=False)
+                else:
+                    monkeypatch.setenv("GNX_HOST_PACK_FRAC", frac)
+                Xd, ld = to_device_haplotypes(src)
+                assert ld % 128 == 0 and np.array_equal(Xd.cpu().numpy(), X), (N, Cc, pinned, frac)
+        monkeypatch.delenv("GNX_HOST_PACK_FRAC", raising=False)
+        Y = X.copy()
+        Y[N // 2, Cc // 2] = -7
+        Yd, _ = to_device_haplotypes(Y)
+        assert np.array_equal(Yd.cpu().numpy(), Y)
+        monkeypatch.setenv("GNX_HOST_PACK", "0")
+        Yd, _ = to_device_haplotypes(Y)
+        assert np.array_equal(Yd.cpu().numpy(), Y)
+        monkeypatch.delenv("GNX_HOST_PACK")
