@@ -253,7 +253,10 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
                 }
                 team_sync(team);
                 // rows straddling w: re-evaluate (Smoother.predict, smooth.py:58-61)
-                // (splitting the work into (row, class) tasks to balance the team was measured: no gain)
+                // (ncu source view: this loop is 70 % of the kernel's instructions and the barrier behind it 31 % of
+                // its stall samples; splitting the work into (row, class) tasks pulled from a team counter keeps all
+                // 8 warps busy but measured the same 357 ms in an in-process A/B -- the SM's issue slots are shared
+                // with the other two teams, so balance inside one team does not shorten the whole)
                 const int nrows = r_hi - r_lo + 1;
                 for (int task = tid; task < 2 * nrows; task += GF_TEAM) {
                     const int h = task / nrows, rr = task - h * nrows;
