@@ -101,12 +101,13 @@ def run_inference(base_args, model, snp_level=False, bed_file_output=False, verb
     X_query, vcf_idx, fmt_idx = gio.vcf_to_npy(vcf, model.snp_pos, model.snp_ref, return_idx=True, verbose=verbose)
     if verbose:
         print("Inferring ancestry on query data...")
-    B_query = model.base.predict_proba(X_query)
+    # gnomix.py:55-60 computes B on the host and hands it to the smoother / to phase(); here both stages run
+    # back to back on the device (Gnomix.predict_proba / phase with B=None): same values, no round trip of B
     if not base_args["phase"]:
-        y_proba = model.smooth.predict_proba(B_query)
+        y_proba = model.predict_proba(X_query)
         y_pred = np.argmax(y_proba, axis=-1)
     else:
-        X_phased, y_pred = model.phase(X_query, B=B_query)
+        X_phased, y_pred = model.phase(X_query)
         U = {"variants/REF": np.asarray(model.snp_ref)[fmt_idx],
              "variants/ALT": np.asarray(model.snp_alt)[fmt_idx].reshape(len(fmt_idx), 1)}
         vcf_phase = update_vcf(vcf, mask=vcf_idx, Updates=U)

@@ -41,6 +41,8 @@ def phase_all(model, X, B=None, max_it=50, verbose=False, want_tracker=False):
         ld = Xv.stride(0)
     if B is None:
         Bd = model.base._device_predict(Xv, ld)
+        if Bd.dtype != torch.float32:      # the string-kernel base returns float64; the tree smoother reads float32
+            Bd = Bd.to(torch.float32)
     elif _is_torch(B):
         Bd = B[:2 * n].to(device="cuda", dtype=torch.float32).clone()
     else:

@@ -133,13 +133,33 @@ class Gnomix:
         self.save()
         self.time["training"] = round(time() - train_time_begin, 2)
 
+    def _base_on_device(self, X):
+        """Base stage with the result left in HBM in the dtype the smoother consumes (float32 for the tree
+        smoother, float64 for the CRF): the same values the reference's two numpy hand-offs produce, without
+        the device -> host -> device round trip of B.  Host matrices are uploaded through the packed transfer."""
+        from .base import to_device_haplotypes
+        Xd, _ = to_device_haplotypes(X)
+        if getattr(self.smooth, "b_dtype", "float32") == "float64" and hasattr(self.base, "predict_proba_f64"):
+            return self.base.predict_proba_f64(Xd)
+        return self.base.predict_proba(Xd)
+
     def predict(self, X):
-        B = self.base.predict_proba(X)
-        return self.smooth.predict(B)
+        """src/model.py:169-173."""
+        if hasattr(X, "is_cuda") and X.is_cuda:
+            return self.smooth.predict(self.base.predict_proba(X))
+        import torch
+        y = self.smooth.predict(self._base_on_device(X))
+        torch.cuda.current_stream().synchronize()
+        return y.cpu().numpy().astype(np.int64)
 
     def predict_proba(self, X):
-        B = self.base.predict_proba(X)
-        return self.smooth.predict_proba(B)
+        """src/model.py:175-179."""
+        if hasattr(X, "is_cuda") and X.is_cuda:
+            return self.smooth.predict_proba(self.base.predict_proba(X))
+        import torch
+        p = self.smooth.predict_proba(self._base_on_device(X))
+        torch.cuda.current_stream().synchronize()
+        return p.cpu().numpy()
 
     def write_config(self, fname):
         with open(fname, "w") as f:

@@ -196,6 +196,8 @@ class CRFModel:
 class CRF_Smoother(Smoother):
     """src/Smooth/models.py:27-32 (+ src/Smooth/crf.py).  proba = CRF marginals (float64)."""
 
+    b_dtype = "float64"   # the reference hands the CRF the base's float64 probabilities (Gnomix keeps them so on the device)
+
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.model = None

@@ -79,3 +79,38 @@ def test_train_pickle_infer_roundtrip(tmp_path):
     assert Xp.shape == Xq.shape
     # phasing only exchanges alleles between the two haplotypes of an individual
     assert np.array_equal(np.sort(np.stack([Xp[0::2], Xp[1::2]]), axis=0), np.sort(np.stack([Xq[0::2], Xq[1::2]]), axis=0))
+
+
+def test_gnomix_predict_numpy_equals_two_step_handoff():
+    """Gnomix.predict / predict_proba on a numpy matrix (src/model.py:169-179) keep B in HBM between the stages;
+    the results equal the reference's two numpy hand-offs (base.predict_proba -> smooth.predict_proba) bit for bit,
+    for the tree smoother (float32 B), the CRF smoother (float64 B) and with a calibrator."""
+    import numpy as np
+    from gnomix_b200 import Gnomix, GBTForest
+    from gnomix_b200.smooth import CRF_Smoother, CRFModel
+    from tests import util
+    rng = np.random.default_rng(17)
+    C, M, A, S, N = 30_011, 500, 7, 15, 333
+    model = Gnomix(C, M, A, S)
+    coefs, icpts, _ = util.random_lr(rng, C, M, A)
+    model.base.set_window_weights(coefs, icpts)
+    model.smooth.model = GBTForest.random(rng, A, model.smooth.S, n_rounds=20, depth=4)
+    X = util.random_haplotypes(rng, N, C)
+    B = model.base.predict_proba(X)
+    assert B.dtype == np.float64
+    p2, y2 = model.smooth.predict_proba(B), model.smooth.predict(B)
+    p1, y1 = model.predict_proba(X), model.predict(X)
+    assert p1.dtype == p2.dtype == np.float32 and np.array_equal(p1, p2)
+    assert y1.dtype == np.int64 and np.array_equal(y1, y2)
+    # calibrated
+    np.random.seed(1)
+    model.smooth.calibrate = True
+    model.smooth.train_calibrator(B[:200], np.argmax(B[:200], axis=-1), frac=0.5)
+    assert np.array_equal(model.predict_proba(X), model.smooth.predict_proba(B)) and np.array_equal(model.predict(X), model.smooth.predict(B))
+    # CRF smoother: float64 hand-off
+    crf = CRF_Smoother(n_windows=C // M, num_ancestry=A, smooth_window_size=S)
+    crf.model = CRFModel(rng.normal(0, 1.5, (A, A)), rng.normal(0, 1.0, (A, A)))
+    model.smooth = crf
+    p2, y2 = crf.predict_proba(B), crf.predict(B)
+    p1, y1 = model.predict_proba(X), model.predict(X)
+    assert p1.dtype == np.float64 and np.array_equal(p1, p2) and np.array_equal(y1, y2)
