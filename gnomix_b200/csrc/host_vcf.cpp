@@ -29,15 +29,19 @@ void set_error(const char* fmt, ...);
 }
 
 struct gnx_vcf {
-    std::vector<char> text;
+    char* text = nullptr;           // the whole (inflated) file, newline-terminated; malloc'ed (no zero fill)
+    size_t text_len = 0, text_cap = 0;
     std::vector<std::string> samples;
     int64_t n_rec = 0, n_smp = 0;
-    std::vector<int8_t> gt;         // [n_rec][n_smp][2]
-    std::vector<int32_t> pos;
-    std::vector<float> qual;
+    int threads = 0;
+    std::vector<int64_t> ls;        // line starts of candidate records
+    std::vector<uint8_t> keep;      // per candidate line: a record we keep
+    std::vector<int64_t> blk_count; // kept records before each block of lines
+    bool parsed = false;            // pass B done (string spans known)
     // string columns as (offset, length) into text: CHROM, ID, REF, ALT (whole column)
     std::vector<int64_t> off[4];
     std::vector<int32_t> len[4];
+    ~gnx_vcf() { free(text); }
 };
 
 namespace {
@@ -93,7 +97,7 @@ int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads
     }
     *out = nullptr;
     gnx_vcf* v = new gnx_vcf();
-    std::vector<char>& text = v->text;
+    v->threads = threads;
     size_t n = 0;
     {
         // plain text is read directly; gzip / bgzip (magic 1f 8b) is inflated by zlib
@@ -106,45 +110,51 @@ int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads
         unsigned char magic[2] = {0, 0};
         const size_t mg = fread(magic, 1, 2, fp);
         fseek(fp, 0, SEEK_END);
-        const long fsize = ftell(fp);
+        const long fsize = std::max<long>(ftell(fp), 0);
         fseek(fp, 0, SEEK_SET);
         const bool gz = (mg == 2 && magic[0] == 0x1f && magic[1] == 0x8b);
+        auto grow = [&](size_t cap) -> bool {
+            char* p = static_cast<char*>(realloc(v->text, cap));
+            if (!p) return false;
+            v->text = p;
+            v->text_cap = cap;
+            return true;
+        };
+        bool ok = true;
         if (!gz) {
-            text.resize((size_t)std::max<long>(fsize, 0) + 2);
-            n = fread(text.data(), 1, (size_t)std::max<long>(fsize, 0), fp);
+            ok = grow((size_t)fsize + 2);
+            if (ok) n = fread(v->text, 1, (size_t)fsize, fp);
             fclose(fp);
         } else {
             fclose(fp);
             gzFile f = gzopen(path, "rb");
-            if (!f) {
-                delete v;
-                gnx::set_error("gnx_vcf_open: cannot open %s", path);
-                return 1;
-            }
-            gzbuffer(f, 1u << 20);
-            text.resize(std::max<size_t>(size_t(64) << 20, (size_t)fsize * 8));  // VCF genotype text inflates ~6x
-            for (;;) {
-                if (text.size() - n < (size_t(8) << 20)) text.resize(text.size() * 2);
-                const int got = gzread(f, text.data() + n, (unsigned)std::min<size_t>(text.size() - n, size_t(1) << 30));
-                if (got < 0) {
-                    gzclose(f);
-                    delete v;
-                    gnx::set_error("gnx_vcf_open: read error in %s", path);
-                    return 1;
+            ok = f != nullptr && grow(std::max<size_t>(size_t(64) << 20, (size_t)fsize * 8));  // genotype text inflates ~6x
+            if (f) {
+                gzbuffer(f, 1u << 20);
+                while (ok) {
+                    if (v->text_cap - n < (size_t(8) << 20)) ok = grow(v->text_cap * 2);
+                    if (!ok) break;
+                    const int got = gzread(f, v->text + n, (unsigned)std::min<size_t>(v->text_cap - n - 2, size_t(1) << 30));
+                    if (got < 0) ok = false;
+                    if (got <= 0) break;
+                    n += (size_t)got;
                 }
-                if (got == 0) break;
-                n += (size_t)got;
+                gzclose(f);
             }
-            gzclose(f);
+        }
+        if (!ok) {
+            delete v;
+            gnx::set_error("gnx_vcf_open: cannot read %s (I/O error or out of memory)", path);
+            return 1;
         }
     }
-    if (n == 0 || text[n - 1] != '\n') text[n++] = '\n';
-    text.resize(n);
-    const char* base = text.data();
+    if (n == 0 || v->text[n - 1] != '\n') v->text[n++] = '\n';
+    v->text_len = n;
+    const char* base = v->text;
     const char* end = base + n;
 
     // ---- line index (records only), header
-    std::vector<int64_t> ls;  // line starts of candidate records
+    std::vector<int64_t>& ls = v->ls;
     {
         const char* p = base;
         while (p < end) {
@@ -174,10 +184,12 @@ int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads
     const size_t chm_len = chm ? strlen(chm) : 0;
 
     // ---- pass A: which lines are records we keep (>= 10 columns, CHROM filter)
-    std::vector<uint8_t> keep((size_t)nl_total, 0);
+    std::vector<uint8_t>& keep = v->keep;
+    keep.assign((size_t)nl_total, 0);
     const int64_t blk = 4096;
     const int64_t nblk = (nl_total + blk - 1) / blk;
-    std::vector<int64_t> blk_count((size_t)nblk + 1, 0);
+    std::vector<int64_t>& blk_count = v->blk_count;
+    blk_count.assign((size_t)nblk + 1, 0);
     gnx::parallel_for(nblk, threads, [&](int64_t b) {
         int64_t cnt = 0;
         for (int64_t i = b * blk; i < std::min(nl_total, (b + 1) * blk); i++) {
@@ -200,23 +212,38 @@ int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads
         blk_count[b + 1] = cnt;
     });
     for (int64_t b = 0; b < nblk; b++) blk_count[b + 1] += blk_count[b];
-    const int64_t R = blk_count[nblk], S = v->n_smp;
-    v->n_rec = R;
-    v->gt.assign((size_t)R * S * 2, -1);
-    v->pos.resize((size_t)R);
-    v->qual.resize((size_t)R);
+    v->n_rec = blk_count[nblk];
+    *out = v;
+    return 0;
+}
+
+void gnx_vcf_close(gnx_vcf_t* v) { delete v; }
+
+int64_t gnx_vcf_num_records(const gnx_vcf_t* v) { return v ? v->n_rec : -1; }
+int64_t gnx_vcf_num_samples(const gnx_vcf_t* v) { return v ? v->n_smp : -1; }
+
+/* Pass B: parses the kept records straight into the caller's arrays -- gt [records][samples][2] int8
+ * (-1 = missing), pos [records] int32, qual [records] float32; any may be NULL -- and records where the
+ * string columns sit. */
+int gnx_vcf_copy(const gnx_vcf_t* vc, int8_t* gt, int32_t* pos, float* qual) {
+    if (!vc) return 2;
+    gnx_vcf* v = const_cast<gnx_vcf*>(vc);
+    const int64_t R = v->n_rec, S = v->n_smp;
+    const char* base = v->text;
+    const char* end = base + v->text_len;
+    const int64_t nl_total = (int64_t)v->ls.size();
+    const int64_t blk = 4096;
+    const int64_t nblk = (nl_total + blk - 1) / blk;
     for (int k = 0; k < 4; k++) {
         v->off[k].resize((size_t)R);
         v->len[k].resize((size_t)R);
     }
     std::atomic<int> bad_pos{0};
-
-    // ---- pass B: parse
-    gnx::parallel_for(nblk, threads, [&](int64_t b) {
-        int64_t r = blk_count[b];
+    gnx::parallel_for(nblk, v->threads, [&](int64_t b) {
+        int64_t r = v->blk_count[b];
         for (int64_t i = b * blk; i < std::min(nl_total, (b + 1) * blk); i++) {
-            if (!keep[i]) continue;
-            const char* p = base + ls[i];
+            if (!v->keep[i]) continue;
+            const char* p = base + v->ls[i];
             const char* e = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
             if (e > p && e[-1] == '\r') e--;
             const char* col[10];
@@ -234,7 +261,7 @@ int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads
             span(2, 1);  // ID
             span(3, 2);  // REF
             span(4, 3);  // ALT
-            {
+            if (pos) {
                 long long pv = 0;
                 const char* s = col[1];
                 const char* se = col[2] - 1;
@@ -242,53 +269,43 @@ int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads
                 for (; s < se; s++) {
                     if (*s < '0' || *s > '9') { ok = false; break; }
                     pv = pv * 10 + (*s - '0');
+                    if (pv > 2147483647LL) { ok = false; break; }
                 }
-                if (!ok || pv > 2147483647LL) bad_pos.store(1);
-                v->pos[r] = (int32_t)pv;
+                if (!ok) bad_pos.store(1);
+                pos[r] = (int32_t)pv;
             }
-            {
+            if (qual) {
                 const char* s = col[5];
                 const char* se = col[6] - 1;
                 if (se - s == 0 || (se - s == 1 && *s == '.')) {
-                    v->qual[r] = NAN;
+                    qual[r] = NAN;
                 } else {
                     char tmp[64];
                     const size_t l = std::min<size_t>((size_t)(se - s), sizeof tmp - 1);
                     memcpy(tmp, s, l);
                     tmp[l] = 0;
-                    v->qual[r] = strtof(tmp, nullptr);
+                    qual[r] = strtof(tmp, nullptr);
                 }
             }
-            int8_t* g = v->gt.data() + (size_t)r * S * 2;
-            const char* s = col[9];
-            for (int64_t k = 0; k < S && s <= e; k++) {
-                const char* t = find_tab(s, e);
-                parse_gt(s, t, g + 2 * k);
-                s = t + 1;
+            if (gt) {
+                int8_t* g = gt + (size_t)r * S * 2;
+                const char* s = col[9];
+                int64_t k = 0;
+                for (; k < S && s <= e; k++) {
+                    const char* t = find_tab(s, e);
+                    parse_gt(s, t, g + 2 * k);
+                    s = t + 1;
+                }
+                for (; k < S; k++) g[2 * k] = g[2 * k + 1] = -1;   // short record: missing calls
             }
             r++;
         }
     });
+    v->parsed = true;
     if (bad_pos.load()) {
-        delete v;
-        gnx::set_error("gnx_vcf_open: a POS column of %s is not a non-negative 32-bit integer", path);
+        gnx::set_error("gnx_vcf_copy: a POS column is not a non-negative 32-bit integer");
         return 1;
     }
-    *out = v;
-    return 0;
-}
-
-void gnx_vcf_close(gnx_vcf_t* v) { delete v; }
-
-int64_t gnx_vcf_num_records(const gnx_vcf_t* v) { return v ? v->n_rec : -1; }
-int64_t gnx_vcf_num_samples(const gnx_vcf_t* v) { return v ? v->n_smp : -1; }
-
-/* gt [records][samples][2] int8 (-1 = missing), pos [records] int32, qual [records] float32; any may be NULL */
-int gnx_vcf_copy(const gnx_vcf_t* v, int8_t* gt, int32_t* pos, float* qual) {
-    if (!v) return 2;
-    if (gt && !v->gt.empty()) memcpy(gt, v->gt.data(), v->gt.size());
-    if (pos && v->n_rec) memcpy(pos, v->pos.data(), sizeof(int32_t) * (size_t)v->n_rec);
-    if (qual && v->n_rec) memcpy(qual, v->qual.data(), sizeof(float) * (size_t)v->n_rec);
     return 0;
 }
 
@@ -296,6 +313,7 @@ int gnx_vcf_copy(const gnx_vcf_t* v, int8_t* gt, int32_t* pos, float* qual) {
  * Writes every string followed by a newline into buf (if cap suffices); returns the bytes needed. */
 int64_t gnx_vcf_strings(const gnx_vcf_t* v, int field, char* buf, int64_t cap) {
     if (!v || field < 0 || field > 4) return -1;
+    if (field < 4 && !v->parsed && gnx_vcf_copy(v, nullptr, nullptr, nullptr)) return -1;
     int64_t need = 0;
     if (field == 4) {
         for (const auto& s : v->samples) need += (int64_t)s.size() + 1;
@@ -313,7 +331,7 @@ int64_t gnx_vcf_strings(const gnx_vcf_t* v, int field, char* buf, int64_t cap) {
     if (buf && cap >= need) {
         int64_t o = 0;
         for (int64_t r = 0; r < v->n_rec; r++) {
-            memcpy(buf + o, v->text.data() + v->off[field][r], (size_t)v->len[field][r]);
+            memcpy(buf + o, v->text + v->off[field][r], (size_t)v->len[field][r]);
             o += v->len[field][r];
             buf[o++] = '\n';
         }

@@ -242,10 +242,11 @@ int64_t gnx_format_floats(const void* values, int is_f64, int64_t n, char* out, 
  * Host-side input of run_inference: VCF(.gz) -> genotype calls
  * replaces: allel.read_vcf behind read_vcf (src/utils.py:55-81) for the fields the reference
  *           reads (calldata/GT, variants/POS|REF|ALT|CHROM|ID|QUAL, samples).
- * gnx_vcf_open inflates the file (plain / gzip / bgzip), keeps the records whose CHROM equals
- * `chm` (NULL: all) and parses them on `threads` host threads (<= 0: gnx_host_threads()).
- * gnx_vcf_copy: gt [records][samples][2] int8 (-1 = missing or haploid second allele),
- * pos [records] int32, qual [records] float32 (NaN for '.'); any pointer may be NULL.
+ * gnx_vcf_open reads / inflates the file (plain / gzip / bgzip), indexes its lines and selects
+ * the records whose CHROM equals `chm` (NULL: all); `threads` <= 0: gnx_host_threads().
+ * gnx_vcf_copy parses them in parallel straight into the caller's arrays: gt [records]
+ * [samples][2] int8 (-1 = missing or haploid second allele), pos [records] int32, qual
+ * [records] float32 (NaN for '.'); any pointer may be NULL.
  * gnx_vcf_strings: field 0 CHROM, 1 ID, 2 REF, 3 ALT (comma-separated as in the file),
  * 4 sample names; every string followed by a newline is written into buf when cap suffices;
  * returns the bytes needed (call with buf = NULL first).
