@@ -74,9 +74,10 @@ gbt_smooth_rank_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
         for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     // VAR 2 (wide): lower uint2 [T][12] | leaves [T][16];  VAR 0/1: lower u32 [T][12] | leaves | top uint4 [T]
-    constexpr int NODE_B = (VAR == 2) ? 8 : 4;
+    // VAR 4 (accumulating offset): block u32 [T][16] | leaves [T][16]
+    constexpr int LOWER_B = (VAR == 2) ? RK_LOWER * 8 : (VAR == 4) ? RK_BLOCK * 4 : RK_LOWER * 4;
     const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
-    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * RK_LOWER * NODE_B);
+    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * LOWER_B);
     const uint4* top_s = reinterpret_cast<const uint4*>(smem + (size_t)m.T * (RK_LOWER + RK_LEAVES) * 4);
     (void)top_s;
     uint32_t* rk = reinterpret_cast<uint32_t*>(smem + forest_bytes);
@@ -138,6 +139,8 @@ gbt_smooth_rank_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
                 if constexpr (VAR == 2)
                     gbt_rank_walk_w<AT>(A, row, topc, reinterpret_cast<const unsigned char*>(lower_s),
                                         reinterpret_cast<const unsigned char*>(leaves_s), rounds, psum);
+                else if constexpr (VAR == 4)
+                    gbt_rank_walk_o<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
                 else if constexpr (VAR == 1)
                     gbt_rank_walk_c<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
                 else
@@ -174,7 +177,7 @@ gbt_rank_u16_kernel(const float* __restrict__ thr, int K, int table_in_smem, con
 
 // K4b: tile = 32 haplotypes (lane = haplotype) x Lseg windows (warp = window); the rank tile is
 // lane-interleaved in shared memory (see gbt_rank_walk_t), the forest sits next to it.
-template <int AT>
+template <int AT, bool BLOCK>
 __global__ void __launch_bounds__(RK_THREADS, 1)
 gbt_smooth_tile_kernel(const __grid_constant__ GbtTopW topc, GbtDev m, const unsigned char* __restrict__ forest_img,
                        size_t forest_bytes, const uint16_t* __restrict__ R, const float* __restrict__ B, int64_t N, int W,
@@ -188,7 +191,7 @@ gbt_smooth_tile_kernel(const __grid_constant__ GbtTopW topc, GbtDev m, const uns
         for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
-    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * RK_LOWER * 4);
+    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * (BLOCK ? RK_BLOCK : RK_LOWER) * 4);
     uint32_t* tile = reinterpret_cast<uint32_t*>(smem + forest_bytes);
     const int pad = (m.S + 1) / 2;
     const int Lslots = Lseg + m.S - 1;
@@ -239,7 +242,8 @@ gbt_smooth_tile_kernel(const __grid_constant__ GbtTopW topc, GbtDev m, const uns
             if (w >= W) break;
             const uint32_t row = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)(wl * A * 128 + lane * 4);
             float psum[AMAX];
-            gbt_rank_walk_t<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
+            if constexpr (BLOCK) gbt_rank_walk_to<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
+            else gbt_rank_walk_t<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
             if (n < N) gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
         }
     }
@@ -417,6 +421,8 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->h_topt = nullptr;
     m->tile_forest = nullptr;
     m->tile_forest_bytes = 0;
+    m->tblock_forest = nullptr;
+    m->tblock_forest_bytes = 0;
     if (rank_ok && n_trees <= GBT_TOPW_MAX_T && K <= 65534 && F <= 65535) {
         std::vector<uint32_t> timg((size_t)n_trees * (RK_LOWER + RK_LEAVES), 0u);
         m->h_topt = new GbtTopW();
@@ -440,6 +446,39 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
         }
         m->tile_forest = static_cast<const unsigned char*>(d_t);
         m->tile_forest_bytes = timg.size() * 4;
+        std::vector<uint32_t> tb((size_t)n_trees * (RK_BLOCK + RK_LEAVES), 0u);
+        for (int t = 0; t < n_trees; t++) {
+            for (int i2 = 0; i2 < 4; i2++) tb[(size_t)t * RK_BLOCK + 4 * i2] = timg[(size_t)t * RK_LOWER + i2];
+            for (int i3 = 0; i3 < 8; i3++) tb[(size_t)t * RK_BLOCK + 2 * i3 + 1] = timg[(size_t)t * RK_LOWER + 4 + i3];
+        }
+        memcpy(tb.data() + (size_t)n_trees * RK_BLOCK, timg.data() + (size_t)n_trees * RK_LOWER, sizeof(uint32_t) * (size_t)n_trees * RK_LEAVES);
+        void* d_tb = nullptr;
+        if (cudaMalloc(&d_tb, tb.size() * 4) != cudaSuccess || cudaMemcpy(d_tb, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("gnx_gbt_model_create: tile block image allocation failed");
+            return 1;
+        }
+        m->tblock_forest = static_cast<const unsigned char*>(d_tb);
+        m->tblock_forest_bytes = tb.size() * 4;
+    }
+    // block image (accumulating-offset variant): per tree 16 words -- level-2 node i2 at word 4 * i2, level-3 node
+    // i3 at word 2 * i3 + 1 -- then the leaves
+    m->block_forest = nullptr;
+    m->block_forest_bytes = 0;
+    if (rank_ok && n_trees <= GBT_TOPC_MAX_T) {
+        std::vector<uint32_t> bimg((size_t)n_trees * (RK_BLOCK + RK_LEAVES), 0u);
+        const uint32_t* lower = rimg.data();
+        for (int t = 0; t < n_trees; t++) {
+            for (int i2 = 0; i2 < 4; i2++) bimg[(size_t)t * RK_BLOCK + 4 * i2] = lower[(size_t)t * RK_LOWER + i2];
+            for (int i3 = 0; i3 < 8; i3++) bimg[(size_t)t * RK_BLOCK + 2 * i3 + 1] = lower[(size_t)t * RK_LOWER + 4 + i3];
+        }
+        memcpy(bimg.data() + (size_t)n_trees * RK_BLOCK, rimg.data() + (size_t)n_trees * RK_LOWER, sizeof(uint32_t) * (size_t)n_trees * RK_LEAVES);
+        void* d_b = nullptr;
+        if (cudaMalloc(&d_b, bimg.size() * 4) != cudaSuccess || cudaMemcpy(d_b, bimg.data(), bimg.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("gnx_gbt_model_create: block image allocation failed");
+            return 1;
+        }
+        m->block_forest = static_cast<const unsigned char*>(d_b);
+        m->block_forest_bytes = bimg.size() * 4;
     }
     m->h_topw = nullptr;
     m->wide_forest = reinterpret_cast<const unsigned char*>(blob + forest + 256 + rb + tb);
@@ -450,12 +489,13 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
         for (int t = 0; t < n_trees; t++)
             for (int k = 0; k < 3; k++) m->h_topw->w[3 * t + k] = make_uint2(top[(size_t)t * 4 + k] & 0xffff0000u, top[(size_t)t * 4 + k] & 0xffffu);
     }
-    // measured on B200 (chr1 x 50 000): narrow + parameter-bank tops 59.6 ms, wide nodes 63.0 ms (LDS.64 costs two
-    // shared-memory wavefronts and the kernel is wavefront/issue co-limited) -> narrow is the default
-    m->variant = m->h_topc ? 1 : 0;
+    // measured on B200 (chr1 x 20 000 haplotypes, scripts/k4_probe.py): accumulating-offset block layout 22.7 ms,
+    // one-word nodes + byte-offset walk 23.7 ms, two-word nodes 25.4 ms (LDS.64 costs two shared-memory wavefronts
+    // and the kernel is wavefront / issue co-limited), lane-interleaved tiles 25.7 ms, tiles + block layout 26.8 ms
+    m->variant = (m->block_forest && m->h_topc) ? 4 : (m->h_topc ? 1 : 0);
     if (const char* e = getenv("GNX_GBT_VARIANT")) {  // profiling / cross-check switch
         const int v = atoi(e);
-        if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt)) m->variant = v;
+        if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt) || (v == 4 && m->block_forest) || (v == 5 && m->tblock_forest)) m->variant = v;
     }
     *out = m;
     return 0;
@@ -465,6 +505,8 @@ void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     if (!m) return;
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->tile_forest) cudaFree(const_cast<unsigned char*>(m->tile_forest));
+    if (m->block_forest) cudaFree(const_cast<unsigned char*>(m->block_forest));
+    if (m->tblock_forest) cudaFree(const_cast<unsigned char*>(m->tblock_forest));
     delete m->h_topt;
     delete m->h_topw;
     delete m->h_topc;
@@ -494,15 +536,18 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bp_bytes = (size_t)(W + 2 * pad) * m->d.A * sizeof(float);
     const size_t smem_max = 227 * 1024;
-    if (m->d.rank_ok && m->use_rank && m->variant == 3 && m->h_topt) {
+    if (m->d.rank_ok && m->use_rank && (m->variant == 3 || m->variant == 5) && m->h_topt) {
+        const bool blockv = (m->variant == 5);
+        const unsigned char* timgp = blockv ? m->tblock_forest : m->tile_forest;
+        const size_t timgb = blockv ? m->tblock_forest_bytes : m->tile_forest_bytes;
         // tile variant: K4a rank transform into a stream-ordered scratch buffer, K4b tile kernel
         const size_t slot_bytes = (size_t)m->d.A * 128;
-        const size_t room = smem_max - m->tile_forest_bytes - 16;
+        const size_t room = smem_max - timgb - 16;
         const int Lmax = (int)std::min<int64_t>((int64_t)(room / slot_bytes) - (m->d.S - 1), 2 * (RK_THREADS / 32));
         if (Lmax >= 32 || Lmax >= W) {
             const int nseg = (int)ceil_div(W, std::min(Lmax, W));
             const int Lseg = (int)ceil_div(W, nseg);
-            const size_t smem = m->tile_forest_bytes + (size_t)(Lseg + m->d.S - 1) * slot_bytes + 16;
+            const size_t smem = timgb + (size_t)(Lseg + m->d.S - 1) * slot_bytes + 16;
             const int64_t count = N * (int64_t)W * m->d.A;
             uint16_t* R = nullptr;
             GNX_CUDA(cudaMallocAsync((void**)&R, (size_t)count * sizeof(uint16_t), st));
@@ -515,9 +560,15 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
             const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count());
 #define CALLT(AT)                                                                                                              \
     do {                                                                                                                       \
-        GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        gbt_smooth_tile_kernel<AT><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, m->tile_forest, m->tile_forest_bytes, R, \
-                                                                   B_dev, N, W, nseg, Lseg, proba_dev, label_dev);             \
+        if (blockv) {                                                                                                          \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_tile_kernel<AT, true><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
+                                                                             Lseg, proba_dev, label_dev);                     \
+        } else {                                                                                                               \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_tile_kernel<AT, false><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
+                                                                              Lseg, proba_dev, label_dev);                    \
+        }                                                                                                                      \
     } while (0)
             GBT_DISPATCH_A(m->d.A, CALLT)
 #undef CALLT
@@ -531,9 +582,9 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
         // per haplotype when the chromosome fits shared memory; (G, Lseg) chosen for the best fit of
         // rows to the 1024 threads.
         const size_t slot_bytes = (size_t)m->d.astride * 4;
-        const int var = m->variant == 3 ? (m->h_topc ? 1 : 0) : m->variant;  // tile variant not applicable here
-        const size_t img_bytes = (var == 2) ? m->wide_forest_bytes : m->rank_forest_bytes;
-        const unsigned char* img = (var == 2) ? m->wide_forest : m->rank_forest;
+        const int var = (m->variant == 3 || m->variant == 5) ? (m->h_topc ? 1 : 0) : m->variant;  // tile variants not applicable here
+        const size_t img_bytes = (var == 2) ? m->wide_forest_bytes : (var == 4) ? m->block_forest_bytes : m->rank_forest_bytes;
+        const unsigned char* img = (var == 2) ? m->wide_forest : (var == 4) ? m->block_forest : m->rank_forest;
         const size_t room = smem_max - img_bytes - 16;
         int bestG = 0, bestL = 0;
         double best_eff = 0.0;
@@ -561,7 +612,9 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     } while (0)
 #define CALLR(AT)                                                  \
     do {                                                           \
-        if (var == 2) {                                            \
+        if (var == 4) {                                            \
+            LAUNCHR(AT, 4, GbtTopC, *m->h_topc);                   \
+        } else if (var == 2) {                                     \
             LAUNCHR(AT, 2, GbtTopW, *m->h_topw);                   \
         } else if (var == 1) {                                     \
             LAUNCHR(AT, 1, GbtTopC, *m->h_topc);                   \
@@ -599,12 +652,12 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
 
 int gnx_gbt_set_kernel(gnx_gbt_t* m, int which) {
     GNX_REQUIRE(m != nullptr, "gnx_gbt_set_kernel: NULL model");
-    GNX_REQUIRE(which == 0 || which == 1 || (which >= 10 && which <= 13), "gnx_gbt_set_kernel: unknown kernel %d", which);
+    GNX_REQUIRE(which == 0 || which == 1 || (which >= 10 && which <= 15), "gnx_gbt_set_kernel: unknown kernel %d", which);
     if (which >= 10) {  // rank-form flavour: 10 narrow nodes, 11 narrow + parameter-bank tops, 12 wide nodes
         const int v = which - 10;
         m->use_rank = 1;
         if (!m->d.rank_ok) return 0;  // not a rank-form forest: the generic kernel runs whatever the flavour
-        GNX_REQUIRE(v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt), "gnx_gbt_set_kernel: flavour %d not available for this forest", v);
+        GNX_REQUIRE(v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt) || (v == 4 && m->block_forest) || (v == 5 && m->tblock_forest), "gnx_gbt_set_kernel: flavour %d not available for this forest", v);
         m->variant = v;
         m->use_rank = 1;
         return 0;

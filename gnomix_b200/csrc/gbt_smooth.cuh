@@ -199,6 +199,49 @@ __device__ __forceinline__ void gbt_rank_walk_c(int A, const unsigned char* __re
     }
 }
 
+// Accumulating-offset variant (gnx_gbt_set_kernel 14): nodes 3..14 of a tree sit in one 64-byte block laid out so
+// that a single byte offset o = 32 b0 + 16 b1 + 8 b2 + 4 b3 (b = branch bits) addresses every level: level-2 node at
+// block + (32 b0 + 16 b1), level-3 node at block + (32 b0 + 16 b1 + 8 b2) + 4, leaf at leaves + o.  Each level then
+// costs one compare and one predicated add instead of a select and a shift-add.
+constexpr int RK_BLOCK = 16;   // words per tree in the block layout (4 unused)
+__device__ __forceinline__ void gnx_add_if_gt(uint32_t& o, uint32_t x, uint32_t n, uint32_t inc) {
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(o) : "r"(x), "r"(n), "r"(inc));
+}
+
+template <int AT>
+__device__ __forceinline__ void gbt_rank_walk_o(int A, const unsigned char* __restrict__ row, const GbtTopC& top,
+                                                const uint32_t* __restrict__ blk, const float* __restrict__ lv, int rounds,
+                                                float* psum) {
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+    int tbase = 0;
+    const unsigned char* bb = reinterpret_cast<const unsigned char*>(blk);
+    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const uint32_t t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
+                const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (t0 & 0xffffu));
+                const bool b0 = x0 > t0;
+                const uint32_t n1 = b0 ? t2 : t1;
+                uint32_t o = b0 ? 32u : 0u;
+                gnx_add_if_gt(o, *reinterpret_cast<const uint32_t*>(row + (n1 & 0xffffu)), n1, 16u);
+                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + o);
+                gnx_add_if_gt(o, *reinterpret_cast<const uint32_t*>(row + (n2 & 0xffffu)), n2, 8u);
+                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + 4 + o);
+                gnx_add_if_gt(o, *reinterpret_cast<const uint32_t*>(row + (n3 & 0xffffu)), n3, 4u);
+                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
+            }
+        }
+        tbase += 3 * A;
+        bb += RK_BLOCK * 4 * A;
+        lvb += RK_LEAVES * 4 * A;
+    }
+}
+
 constexpr int GBT_TOPW_MAX_T = 1024;
 struct GbtTopW {
     uint2 w[3 * GBT_TOPW_MAX_T];
@@ -245,6 +288,40 @@ __device__ __forceinline__ void gbt_rank_walk_t(int A, uint32_t row, const GbtTo
         }
         tbase += 3 * A;
         lwb += RK_LOWER * 4 * A;
+        lvb += RK_LEAVES * 4 * A;
+    }
+}
+
+// Tile walk with the accumulating-offset block layout (gnx_gbt_set_kernel 15): conflict-free feature loads
+// and one predicated add per level.
+template <int AT>
+__device__ __forceinline__ void gbt_rank_walk_to(int A, uint32_t row, const GbtTopW& top, const uint32_t* __restrict__ blk,
+                                                 const float* __restrict__ lv, int rounds, float* psum) {
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+    int tbase = 0;
+    const unsigned char* bb = reinterpret_cast<const unsigned char*>(blk);
+    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const uint2 t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
+                const bool b0 = gnx_lds_u32(row + t0.y) > t0.x;
+                const uint2 n1 = b0 ? t2 : t1;
+                uint32_t o = b0 ? 32u : 0u;
+                gnx_add_if_gt(o, gnx_lds_u32(row + n1.y), n1.x, 16u);
+                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + o);
+                gnx_add_if_gt(o, gnx_lds_u32(row + ((n2 & 0xffffu) << 7)), n2, 8u);
+                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + 4 + o);
+                gnx_add_if_gt(o, gnx_lds_u32(row + ((n3 & 0xffffu) << 7)), n3, 4u);
+                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
+            }
+        }
+        tbase += 3 * A;
+        bb += RK_BLOCK * 4 * A;
         lvb += RK_LEAVES * 4 * A;
     }
 }
@@ -322,5 +399,9 @@ struct gnx_gbt {
     gnx::GbtTopW* h_topt;    // tile variant: top nodes { k << 16, feat * 128 } (parameter bank) ...
     const unsigned char* tile_forest;  // ... and lower u32 [T][12] | leaves [T][16], node = (k << 16) | feat
     size_t tile_forest_bytes;
+    const unsigned char* tblock_forest; // tile + accumulating-offset variant: block u32 [T][16] (feature-index form) | leaves
+    size_t tblock_forest_bytes;
+    const unsigned char* block_forest;  // accumulating-offset variant: block u32 [T][16] | leaves [T][16]
+    size_t block_forest_bytes;
     int variant;             // rank-form flavour: 2 wide nodes (default when eligible), 1 narrow + parameter-bank tops, 0 narrow
 };
