@@ -349,10 +349,10 @@ def run_ours(args):
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": kernels[dom]["frac_hbm"], "traffic": traffic.get(dom), "peak_source": peak_src,
                      # what actually bounds K4 (ncu --set full of this command, profiles/r1_ncu_final_summary.txt)
-                     "issue_slot_frac": 0.89 if dom.startswith("K4") else None,
-                     "shared_wavefront_frac": 0.80 if dom.startswith("K4") else None,
+                     "issue_slot_frac": 0.75 if dom.startswith("K4") else None,
+                     "shared_wavefront_frac": 0.84 if dom.startswith("K4") else None,
                      "note": "the smoother (K4) dominates the step and is bound by issue slots / shared-memory wavefronts "
-                             "(ncu: issue-active 89 %, LSU shared wavefronts 80 % of peak), not by HBM; the HBM-bound kernel "
+                             "(ncu: LSU shared wavefronts 84 % of peak, issue-active 75 %), not by HBM; the HBM-bound kernel "
                              "of the path is K1, see roofline_base"},
         "roofline_base": {"kernel": "K1_lr_tc_kernel", "bound": "hbm", "achieved": kernels["K1_lr_tc_kernel"]["gbs"], "peak": peak,
                           "unit": "GB/s", "frac": kernels["K1_lr_tc_kernel"]["frac_hbm"], "traffic": traffic.get("K1_lr_tc_kernel"),
