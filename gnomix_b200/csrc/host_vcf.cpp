@@ -225,9 +225,8 @@ int64_t gnx_vcf_num_samples(const gnx_vcf_t* v) { return v ? v->n_smp : -1; }
 /* Pass B: parses the kept records straight into the caller's arrays -- gt [records][samples][2] int8
  * (-1 = missing), pos [records] int32, qual [records] float32; any may be NULL -- and records where the
  * string columns sit. */
-int gnx_vcf_copy(const gnx_vcf_t* vc, int8_t* gt, int32_t* pos, float* qual) {
-    if (!vc) return 2;
-    gnx_vcf* v = const_cast<gnx_vcf*>(vc);
+int gnx_vcf_copy(gnx_vcf_t* v, int8_t* gt, int32_t* pos, float* qual) {
+    if (!v) return 2;
     const int64_t R = v->n_rec, S = v->n_smp;
     const char* base = v->text;
     const char* end = base + v->text_len;
@@ -311,7 +310,7 @@ int gnx_vcf_copy(const gnx_vcf_t* vc, int8_t* gt, int32_t* pos, float* qual) {
 
 /* String columns: field 0 CHROM, 1 ID, 2 REF, 3 ALT (comma-separated as in the file), 4 sample names.
  * Writes every string followed by a newline into buf (if cap suffices); returns the bytes needed. */
-int64_t gnx_vcf_strings(const gnx_vcf_t* v, int field, char* buf, int64_t cap) {
+int64_t gnx_vcf_strings(gnx_vcf_t* v, int field, char* buf, int64_t cap) {
     if (!v || field < 0 || field > 4) return -1;
     if (field < 4 && !v->parsed && gnx_vcf_copy(v, nullptr, nullptr, nullptr)) return -1;
     int64_t need = 0;

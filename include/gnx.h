@@ -256,8 +256,8 @@ int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads
 void gnx_vcf_close(gnx_vcf_t* v);
 int64_t gnx_vcf_num_records(const gnx_vcf_t* v);
 int64_t gnx_vcf_num_samples(const gnx_vcf_t* v);
-int gnx_vcf_copy(const gnx_vcf_t* v, int8_t* gt, int32_t* pos, float* qual);
-int64_t gnx_vcf_strings(const gnx_vcf_t* v, int field, char* buf, int64_t cap);
+int gnx_vcf_copy(gnx_vcf_t* v, int8_t* gt, int32_t* pos, float* qual);
+int64_t gnx_vcf_strings(gnx_vcf_t* v, int field, char* buf, int64_t cap);
 /* vcf_to_npy after the SNP intersection (src/utils.py:121-153): X[2s+h][fmt_idx[k]] =
  * gt[vcf_idx[k]][s][h], flipped 0 <-> 1 where swap[k] (nullable), everything that is not 0 / 1 and
  * every column outside fmt_idx = miss_fill.  gt [R][S][2] int8, X [2S][ldX] int8 host memory. */
