@@ -3,8 +3,8 @@
 // Replaces the scikit-allel call behind read_vcf (reference src/utils.py:55-81; the fields the
 // reference reads: calldata/GT, variants/POS|REF|ALT|CHROM|ID|QUAL, samples).  The reference's
 // own notebook names this step as the largest part of an inference run (demo.ipynb:236).  The
-// file is inflated with zlib (plain, gzip and bgzip all go through gzread), the line index is
-// built once, and records are parsed in parallel on the library's worker pool straight into the
+// file is read whole (plain text directly; BGZF members inflated in parallel; any other gzip file
+// through one zlib stream), the line index is built once, and records are parsed in parallel on the library's worker pool straight into the
 // int8 [records, samples, 2] genotype block.  Semantics follow gnomix_b200/io.py (which follows
 // allel): '##' lines skipped, '#CHROM' names the samples, records with fewer than 10 columns
 // skipped, optional CHROM filter, GT = text before the first ':' of a sample column, alleles
@@ -86,6 +86,67 @@ inline void parse_gt(const char* p, const char* e, int8_t* out) {
     out[1] = allele(s2, t);
 }
 
+// BGZF (bgzip / tabix files): a series of gzip members of at most 64 KB each, every header carrying an extra
+// field "BC" with the member's compressed size, every trailer its inflated size -- so the members can be
+// found by hopping over the headers and inflated independently, in parallel.  Returns false if the file is
+// not BGZF (the caller falls back to a single gzread stream).
+struct BgzfBlock {
+    size_t src, csize;   // deflate payload inside the file image
+    size_t dst, isize;
+};
+
+bool bgzf_index(const unsigned char* f, size_t n, std::vector<BgzfBlock>& blocks, size_t& total) {
+    size_t p = 0;
+    total = 0;
+    blocks.clear();
+    while (p < n) {
+        if (n - p < 28 || f[p] != 0x1f || f[p + 1] != 0x8b || f[p + 2] != 8 || !(f[p + 3] & 4)) return false;
+        const size_t xlen = f[p + 10] | ((size_t)f[p + 11] << 8);
+        if (n - p < 12 + xlen + 8) return false;
+        size_t bsize = 0, x = p + 12;
+        const size_t xe = p + 12 + xlen;
+        while (x + 4 <= xe) {
+            const size_t slen = f[x + 2] | ((size_t)f[x + 3] << 8);
+            if (f[x] == 'B' && f[x + 1] == 'C' && slen == 2 && x + 6 <= xe) bsize = (f[x + 4] | ((size_t)f[x + 5] << 8)) + 1;
+            x += 4 + slen;
+        }
+        if (bsize == 0 || bsize < 12 + xlen + 8 || p + bsize > n) return false;
+        const size_t isize = f[p + bsize - 4] | ((size_t)f[p + bsize - 3] << 8) | ((size_t)f[p + bsize - 2] << 16) | ((size_t)f[p + bsize - 1] << 24);
+        if (isize > 65536) return false;
+        blocks.push_back(BgzfBlock{p + 12 + xlen, bsize - (12 + xlen) - 8, total, isize});
+        total += isize;
+        p += bsize;
+    }
+    return !blocks.empty();
+}
+
+bool bgzf_inflate(const unsigned char* f, const std::vector<BgzfBlock>& blocks, char* out, int threads) {
+    std::atomic<int> bad{0};
+    const int64_t per = 64;  // members per task
+    const int64_t nb = (int64_t)blocks.size();
+    gnx::parallel_for((nb + per - 1) / per, threads, [&](int64_t t) {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) {
+            bad.store(1);
+            return;
+        }
+        for (int64_t b = t * per; b < std::min(nb, (t + 1) * per); b++) {
+            const BgzfBlock& k = blocks[(size_t)b];
+            if (k.isize == 0) continue;
+            inflateReset(&zs);
+            zs.next_in = const_cast<unsigned char*>(f + k.src);
+            zs.avail_in = (uInt)k.csize;
+            zs.next_out = reinterpret_cast<unsigned char*>(out + k.dst);
+            zs.avail_out = (uInt)k.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0) bad.store(1);
+        }
+        inflateEnd(&zs);
+    });
+    return bad.load() == 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -126,20 +187,37 @@ int gnx_vcf_open(gnx_vcf_t** out, const char* path, const char* chm, int threads
             if (ok) n = fread(v->text, 1, (size_t)fsize, fp);
             fclose(fp);
         } else {
+            // BGZF members inflate in parallel; any other gzip file goes through one zlib stream
+            std::vector<unsigned char> img((size_t)fsize);
+            const size_t got_img = fread(img.data(), 1, (size_t)fsize, fp);
             fclose(fp);
-            gzFile f = gzopen(path, "rb");
-            ok = f != nullptr && grow(std::max<size_t>(size_t(64) << 20, (size_t)fsize * 8));  // genotype text inflates ~6x
-            if (f) {
-                gzbuffer(f, 1u << 20);
-                while (ok) {
-                    if (v->text_cap - n < (size_t(8) << 20)) ok = grow(v->text_cap * 2);
-                    if (!ok) break;
-                    const int got = gzread(f, v->text + n, (unsigned)std::min<size_t>(v->text_cap - n - 2, size_t(1) << 30));
-                    if (got < 0) ok = false;
-                    if (got <= 0) break;
-                    n += (size_t)got;
+            std::vector<BgzfBlock> blocks;
+            size_t total = 0;
+            bool done = false;
+            if (got_img == (size_t)fsize && bgzf_index(img.data(), img.size(), blocks, total)) {
+                ok = grow(total + 2);
+                if (ok && bgzf_inflate(img.data(), blocks, v->text, threads)) {
+                    n = total;
+                    done = true;
                 }
-                gzclose(f);
+            }
+            if (ok && !done) {
+                img.clear();
+                img.shrink_to_fit();
+                gzFile f = gzopen(path, "rb");
+                ok = f != nullptr && grow(std::max<size_t>(size_t(64) << 20, (size_t)fsize * 8));  // genotype text inflates ~6x
+                if (f) {
+                    gzbuffer(f, 1u << 20);
+                    while (ok) {
+                        if (v->text_cap - n < (size_t(8) << 20)) ok = grow(v->text_cap * 2);
+                        if (!ok) break;
+                        const int got = gzread(f, v->text + n, (unsigned)std::min<size_t>(v->text_cap - n - 2, size_t(1) << 30));
+                        if (got < 0) ok = false;
+                        if (got <= 0) break;
+                        n += (size_t)got;
+                    }
+                    gzclose(f);
+                }
             }
         }
         if (!ok) {

@@ -243,7 +243,8 @@ int64_t gnx_format_floats(const void* values, int is_f64, int64_t n, char* out, 
  * Host-side input of run_inference: VCF(.gz) -> genotype calls
  * replaces: allel.read_vcf behind read_vcf (src/utils.py:55-81) for the fields the reference
  *           reads (calldata/GT, variants/POS|REF|ALT|CHROM|ID|QUAL, samples).
- * gnx_vcf_open reads / inflates the file (plain / gzip / bgzip), indexes its lines and selects
+ * gnx_vcf_open reads / inflates the file (plain text; bgzip members in parallel; other gzip
+ * files through one zlib stream), indexes its lines and selects
  * the records whose CHROM equals `chm` (NULL: all); `threads` <= 0: gnx_host_threads().
  * gnx_vcf_copy parses them in parallel straight into the caller's arrays: gt [records]
  * [samples][2] int8 (-1 = missing or haploid second allele), pos [records] int32, qual
