@@ -59,6 +59,8 @@ _SIGS = {
     "gnx_vcf_strings": (c_i64, [c_vp, C.c_int, c_vp, c_i64]),
     "gnx_vcf_to_haplotypes": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, C.c_int]),
     "gnx_write_fb_body": (C.c_int, [C.c_char_p, C.c_int, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp, C.c_int]),
+    "gnx_write_vcf_body": (C.c_int, [C.c_char_p, C.c_int, c_i64, c_i64, c_vp, c_i64, c_vp, C.c_char_p, c_i64, C.c_char_p, c_i64,
+                                     C.c_char_p, c_i64, C.c_char_p, c_i64, C.c_char_p, c_i64, C.c_int]),
     "gnx_format_floats": (c_i64, [c_vp, C.c_int, c_i64, c_vp, c_i64]),
     "gnx_infer_host_rates": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gnx_infer_host_last_transfer": (C.c_int, [C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(c_i64)]),

@@ -57,9 +57,52 @@ def update_vcf(vcf_data, mask=None, Updates=None):
     return out
 
 
+def _vcf_preamble(f, headers, cols):
+    f.write(headers.encode())
+    f.write(b"##fileformat=VCFv4.1\n##source=gnomix.py\n")
+    f.write(b'##FORMAT=<ID=GT,Number=1,Type=String,Description="Phased Genotype">\n')
+    f.write(("#" + "\t".join(cols) + "\n").encode())
+
+
+def _qual_str(q):
+    return "" if (isinstance(q, float) or isinstance(q, np.floating)) and np.isnan(q) else str(q)
+
+
 def npy_to_vcf(data, npy, results_file, headers=""):
-    """The light VCF writer of src/utils.py:247-329: metadata from `data`, genotypes
-    `maternal|paternal` from the int matrix [2n, C]."""
+    """The light VCF writer of src/utils.py:247-329: metadata from `data`, genotypes `maternal|paternal`
+    from the int matrix [2n, C].  The records are written by the library's host threads
+    (gnx_write_vcf_body); npy_to_vcf_py is the per-record Python loop it replaces."""
+    import ctypes as C
+    from . import _lib
+    if results_file.split(".")[-1] not in [".vcf", ".bcf"]:
+        results_file += ".vcf"
+    hap = np.ascontiguousarray(np.asarray(npy).astype(int).astype(np.int8))
+    chmlen = data["calldata/GT"].shape[0]
+    h, c = hap.shape
+    n = h // 2
+    assert chmlen == c, "reference (" + str(chmlen) + ") and numpy matrix (" + str(c) + ") not compatible"
+    samples = list(data["samples"]) if "samples" in data and len(data["samples"]) == n else ["sample%d" % i for i in range(n)]
+    cols = ["CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + [str(s) for s in samples]
+    with open(results_file, "wb") as f:
+        _vcf_preamble(f, headers, cols)
+
+    def blob(values):
+        b = ("\n".join(values) + "\n").encode() if c else b""
+        return b, len(b)
+
+    pos = np.ascontiguousarray(np.asarray(data["variants/POS"]), dtype=np.int64)
+    chrom, chrom_l = blob([str(v) for v in data["variants/CHROM"]])
+    ident, ident_l = blob([str(v) for v in data["variants/ID"]])
+    ref, ref_l = blob([str(v) for v in data["variants/REF"]])
+    alt, alt_l = blob([str(v[0]) for v in data["variants/ALT"]])
+    qual, qual_l = blob([_qual_str(q) for q in data["variants/QUAL"]])
+    _lib.check(_lib.lib().gnx_write_vcf_body(results_file.encode(), 1, c, 2 * n, hap.ctypes.data, c, pos.ctypes.data, chrom, chrom_l,
+                                             ident, ident_l, ref, ref_l, alt, alt_l, qual, qual_l, 0), "gnx_write_vcf_body")
+    return results_file
+
+
+def npy_to_vcf_py(data, npy, results_file, headers=""):
+    """src/utils.py:247-329 with a Python loop over the records (cross-check of the native writer)."""
     if results_file.split(".")[-1] not in [".vcf", ".bcf"]:
         results_file += ".vcf"
     npy = np.asarray(npy).astype(int)
@@ -76,15 +119,11 @@ def npy_to_vcf(data, npy, results_file, headers=""):
     row[:, 2::4] = ord("|")
     row[:, 3::4] = digits[:, 1::2]
     with open(results_file, "wb") as f:
-        f.write(headers.encode())
-        f.write(b"##fileformat=VCFv4.1\n##source=gnomix.py\n")
-        f.write(b'##FORMAT=<ID=GT,Number=1,Type=String,Description="Phased Genotype">\n')
-        f.write(("#" + "\t".join(cols) + "\n").encode())
+        _vcf_preamble(f, headers, cols)
         for i in range(c):
-            q = data["variants/QUAL"][i]
-            qual = "" if (isinstance(q, float) or isinstance(q, np.floating)) and np.isnan(q) else str(q)
             f.write("\t".join([str(data["variants/CHROM"][i]), str(data["variants/POS"][i]), str(data["variants/ID"][i]),
-                               str(data["variants/REF"][i]), str(data["variants/ALT"][i][0]), qual, "PASS", ".", "GT"]).encode())
+                               str(data["variants/REF"][i]), str(data["variants/ALT"][i][0]), _qual_str(data["variants/QUAL"][i]),
+                               "PASS", ".", "GT"]).encode())
             f.write(row[i].tobytes())
             f.write(b"\n")
     return results_file

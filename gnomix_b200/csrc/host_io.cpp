@@ -120,3 +120,109 @@ extern "C" int64_t gnx_format_floats(const void* v, int is_f64, int64_t n, char*
     }
     return pos;
 }
+
+namespace gnx {
+
+// starts of the '\n'-separated fields of a blob holding `count` fields
+static bool split_lines(const char* blob, int64_t len, int64_t count, std::vector<int64_t>& start) {
+    start.resize((size_t)count + 1);
+    int64_t p = 0;
+    for (int64_t i = 0; i < count; i++) {
+        start[i] = p;
+        const char* nl = p < len ? static_cast<const char*>(memchr(blob + p, '\n', (size_t)(len - p))) : nullptr;
+        if (!nl) return false;
+        p = (nl - blob) + 1;
+    }
+    start[count] = p;
+    return true;
+}
+
+}  // namespace gnx
+
+// Appends (or writes) the records of the phased VCF that npy_to_vcf produces (reference src/utils.py:247-329):
+// record j = CHROM POS ID REF ALT QUAL PASS . GT, then for every sample i "hap(2i)|hap(2i+1)" with one character
+// '0' + value per haplotype.  The five string columns arrive as blobs of newline-terminated fields (n_rec fields
+// each), POS as int64, the haplotypes as int8 [n_hap][ld] (column j = record j).
+extern "C" int gnx_write_vcf_body(const char* path, int append, int64_t n_rec, int64_t n_hap, const int8_t* hap, int64_t ld,
+                                  const int64_t* pos, const char* chrom, int64_t chrom_len, const char* id, int64_t id_len,
+                                  const char* ref, int64_t ref_len, const char* alt, int64_t alt_len, const char* qual,
+                                  int64_t qual_len, int threads) {
+    if (!path || n_rec < 0 || n_hap < 0 || (n_hap & 1) || ld < n_rec || (n_rec > 0 && (!pos || !chrom || !id || !ref || !alt || !qual)) ||
+        (n_rec * n_hap > 0 && !hap)) {
+        gnx::set_error("gnx_write_vcf_body: bad arguments");
+        return 2;
+    }
+    std::vector<int64_t> s_chrom, s_id, s_ref, s_alt, s_qual;
+    if (!gnx::split_lines(chrom, chrom_len, n_rec, s_chrom) || !gnx::split_lines(id, id_len, n_rec, s_id) ||
+        !gnx::split_lines(ref, ref_len, n_rec, s_ref) || !gnx::split_lines(alt, alt_len, n_rec, s_alt) ||
+        !gnx::split_lines(qual, qual_len, n_rec, s_qual)) {
+        gnx::set_error("gnx_write_vcf_body: a string column has fewer than %lld fields", (long long)n_rec);
+        return 2;
+    }
+    FILE* f = fopen(path, append ? "ab" : "wb");
+    if (!f) {
+        gnx::set_error("gnx_write_vcf_body: cannot open %s", path);
+        return 1;
+    }
+    if (threads <= 0) threads = gnx::host_threads_default();
+    const int64_t RB = 256;                                   // records per task: 256 contiguous bytes of every haplotype row
+    const int64_t n_samp = n_hap / 2;
+    const int64_t nblk = (n_rec + RB - 1) / RB;
+    const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nblk, threads));
+    std::vector<std::vector<char>> bufs((size_t)batch);
+    int rc = 0;
+    for (int64_t b0 = 0; b0 < nblk && !rc; b0 += batch) {
+        const int64_t nb = std::min(batch, nblk - b0);
+        gnx::parallel_for(nb, threads, [&](int64_t k) {
+            const int64_t r0 = (b0 + k) * RB, rn = std::min(RB, n_rec - r0);
+            size_t fixed = 0;
+            for (int64_t r = r0; r < r0 + rn; r++)
+                fixed += (size_t)((s_chrom[r + 1] - s_chrom[r]) + (s_id[r + 1] - s_id[r]) + (s_ref[r + 1] - s_ref[r]) +
+                                  (s_alt[r + 1] - s_alt[r]) + (s_qual[r + 1] - s_qual[r])) + 40;
+            std::vector<char>& buf = bufs[(size_t)k];
+            buf.resize(fixed + (size_t)rn * (size_t)(4 * n_samp + 1));
+            // genotype text of the block, record-major: gen[r][4 * i .. 4 * i + 3] = '\t' a '|' b
+            std::vector<char> gen((size_t)rn * (size_t)(4 * n_samp));
+            for (int64_t i = 0; i < n_samp; i++) {
+                const int8_t* ha = hap + (2 * i) * ld + r0;
+                const int8_t* hb = hap + (2 * i + 1) * ld + r0;
+                for (int64_t r = 0; r < rn; r++) {
+                    char* g = gen.data() + (size_t)r * (size_t)(4 * n_samp) + 4 * i;
+                    g[0] = '\t';
+                    g[1] = (char)('0' + ha[r]);
+                    g[2] = '|';
+                    g[3] = (char)('0' + hb[r]);
+                }
+            }
+            char* p = buf.data();
+            auto put = [&](const char* blob, const std::vector<int64_t>& st, int64_t r) {
+                const size_t l = (size_t)(st[r + 1] - st[r] - 1);
+                memcpy(p, blob + st[r], l);
+                p += l;
+                *p++ = '\t';
+            };
+            for (int64_t r = r0; r < r0 + rn; r++) {
+                put(chrom, s_chrom, r);
+                p = std::to_chars(p, p + 24, (long long)pos[r]).ptr;
+                *p++ = '\t';
+                put(id, s_id, r);
+                put(ref, s_ref, r);
+                put(alt, s_alt, r);
+                put(qual, s_qual, r);
+                memcpy(p, "PASS\t.\tGT", 9);
+                p += 9;
+                memcpy(p, gen.data() + (size_t)(r - r0) * (size_t)(4 * n_samp), (size_t)(4 * n_samp));
+                p += 4 * n_samp;
+                *p++ = '\n';
+            }
+            buf.resize((size_t)(p - buf.data()));
+        });
+        for (int64_t k = 0; k < nb; k++)
+            if (fwrite(bufs[(size_t)k].data(), 1, bufs[(size_t)k].size(), f) != bufs[(size_t)k].size()) rc = 1;
+    }
+    if (fclose(f) || rc) {
+        gnx::set_error("gnx_write_vcf_body: write to %s failed", path);
+        return 1;
+    }
+    return 0;
+}

@@ -239,6 +239,15 @@ int gnx_infer_host_last_transfer(double* frac, int64_t* h2d_bytes, int64_t* d2h_
 int gnx_write_fb_body(const char* path, int append, const void* proba, int is_f64, int64_t N,
                       int64_t W, int64_t A, const char* const* prefixes, int threads);
 int64_t gnx_format_floats(const void* values, int is_f64, int64_t n, char* out, int64_t cap);
+/* Records of the phased VCF (replaces the per-record loop of npy_to_vcf, src/utils.py:247-329):
+ * record j = CHROM POS ID REF ALT QUAL PASS . GT then "a|b" per sample with one character
+ * '0' + value per haplotype.  String columns are blobs of n_rec newline-terminated fields,
+ * hap is int8 [n_hap][ld] host memory (column j = record j, rows 2i / 2i+1 = sample i). */
+int gnx_write_vcf_body(const char* path, int append, int64_t n_rec, int64_t n_hap, const int8_t* hap,
+                       int64_t ld, const int64_t* pos, const char* chrom, int64_t chrom_len,
+                       const char* id, int64_t id_len, const char* ref, int64_t ref_len,
+                       const char* alt, int64_t alt_len, const char* qual, int64_t qual_len,
+                       int threads);
 /* ---------------------------------------------------------------------------
  * Host-side input of run_inference: VCF(.gz) -> genotype calls
  * replaces: allel.read_vcf behind read_vcf (src/utils.py:55-81) for the fields the reference
