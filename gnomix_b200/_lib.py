@@ -48,6 +48,7 @@ _SIGS = {
     "gnx_gnofix_last_stats": (C.c_int, [c_vp]),
     "gnx_infer_host": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64]),
     "gnx_upload_haplotypes": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64]),
+    "gnx_release_workspace": (C.c_int, []),
     "gnx_pack_rows_host": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, C.c_int, C.POINTER(C.c_int)]),
     "gnx_unpack_dev": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gnx_host_threads": (C.c_int, []),

@@ -373,3 +373,20 @@ extern "C" int gnx_upload_haplotypes(const int8_t* X_host, int64_t N, int64_t ld
     GNX_CUDA(cudaStreamSynchronize(ws.st[1]));
     return 0;
 }
+
+/* Frees the device slots and pinned staging buffers gnx_infer_host / gnx_upload_haplotypes keep between calls
+ * (they are re-created on demand); the calibration is kept. */
+extern "C" int gnx_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    if (g_ws.device >= 0) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != g_ws.device) {
+            cudaSetDevice(g_ws.device);
+            g_ws.release();
+            cudaSetDevice(cur);
+            return 0;
+        }
+    }
+    g_ws.release();
+    return 0;
+}

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GNX_VERSION 100 /* 0.1.0 */
+#define GNX_VERSION 110 /* 0.1.1: packed host transfer, K7, host-side I/O entry points */
 
 typedef struct gnx_lr gnx_lr_t;   /* per-window logistic-regression base (K1) */
 typedef struct gnx_gbt gnx_gbt_t; /* gradient-boosted-tree smoother (K4)      */
@@ -221,6 +221,8 @@ int gnx_unpack_dev(const uint64_t* packed_dev, int64_t n, int64_t pitch_words, i
  * This is how the Python plugins upload a numpy haplotype matrix (Base.predict_proba, phase). */
 int gnx_upload_haplotypes(const int8_t* X_host, int64_t N, int64_t ldX, int64_t C, int8_t* X_dev,
                           int64_t ld_dev);
+/* frees the device slots and pinned staging buffers the two calls above keep between calls */
+int gnx_release_workspace(void);
 /* rates measured by gnx_infer_host's one-off calibration (0 before it ran): host pack
  * rate in GB/s of int8 input, pinned H2D rate in GB/s */
 int gnx_infer_host_rates(double* pack_gbs, double* h2d_gbs);

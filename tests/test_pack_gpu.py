@@ -109,3 +109,4 @@ def test_upload_haplotypes_equals_plain_copy(libgnx, monkeypatch):
         Yd, _ = to_device_haplotypes(Y)
         assert np.array_equal(Yd.cpu().numpy(), Y)
         monkeypatch.delenv("GNX_HOST_PACK")
+        assert libgnx.gnx_release_workspace() == 0          # buffers come back on demand
