@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "gbt_smooth.cuh"
@@ -177,9 +178,9 @@ gbt_rank_u16_kernel(const float* __restrict__ thr, int K, int table_in_smem, con
 
 // K4b: tile = 32 haplotypes (lane = haplotype) x Lseg windows (warp = window); the rank tile is
 // lane-interleaved in shared memory (see gbt_rank_walk_t), the forest sits next to it.
-template <int AT, bool BLOCK>
+template <int AT, bool BLOCK, typename TOPT>
 __global__ void __launch_bounds__(RK_THREADS, 1)
-gbt_smooth_tile_kernel(const __grid_constant__ GbtTopW topc, GbtDev m, const unsigned char* __restrict__ forest_img,
+gbt_smooth_tile_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsigned char* __restrict__ forest_img,
                        size_t forest_bytes, const uint16_t* __restrict__ R, const float* __restrict__ B, int64_t N, int W,
                        int nseg, int Lseg, float* __restrict__ proba, int32_t* __restrict__ label) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -243,7 +244,7 @@ gbt_smooth_tile_kernel(const __grid_constant__ GbtTopW topc, GbtDev m, const uns
             const uint32_t row = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)(wl * A * 128 + lane * 4);
             float psum[AMAX];
             if constexpr (BLOCK) gbt_rank_walk_to<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
-            else gbt_rank_walk_t<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
+            else if constexpr (std::is_same<TOPT, GbtTopW>::value) gbt_rank_walk_t<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
             if (n < N) gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
         }
     }
@@ -419,6 +420,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     }
     // tile image: the narrow image with the feature index in the low half of every node word
     m->h_topt = nullptr;
+    m->h_toptn = nullptr;
     m->tile_forest = nullptr;
     m->tile_forest_bytes = 0;
     m->tblock_forest = nullptr;
@@ -426,6 +428,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     if (rank_ok && n_trees <= GBT_TOPW_MAX_T && K <= 65534 && F <= 65535) {
         std::vector<uint32_t> timg((size_t)n_trees * (RK_LOWER + RK_LEAVES), 0u);
         m->h_topt = new GbtTopW();
+        m->h_toptn = new GbtTopC();
         auto conv = [&](uint32_t word) -> uint32_t {  // (k << 16 | byte offset in a row) -> (k << 16 | feature index)
             const uint32_t off = (word & 0xffffu) / 4u, slot = off / (uint32_t)astride, a = off % (uint32_t)astride;
             return (word & 0xffff0000u) | (slot * (uint32_t)A + a);
@@ -438,6 +441,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
             for (int k = 0; k < 3; k++) {
                 const uint32_t wd = conv(top[(size_t)t * 4 + k]);
                 m->h_topt->w[3 * t + k] = make_uint2(wd & 0xffff0000u, (wd & 0xffffu) * 128u);
+                m->h_toptn->w[3 * t + k] = wd;
             }
         void* d_t = nullptr;
         if (cudaMalloc(&d_t, timg.size() * 4) != cudaSuccess || cudaMemcpy(d_t, timg.data(), timg.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -495,7 +499,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->variant = (m->block_forest && m->h_topc) ? 4 : (m->h_topc ? 1 : 0);
     if (const char* e = getenv("GNX_GBT_VARIANT")) {  // profiling / cross-check switch
         const int v = atoi(e);
-        if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt) || (v == 4 && m->block_forest) || (v == 5 && m->tblock_forest)) m->variant = v;
+        if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt) || (v == 4 && m->block_forest) || ((v == 5 || v == 6) && m->tblock_forest)) m->variant = v;
     }
     *out = m;
     return 0;
@@ -508,6 +512,7 @@ void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     if (m->block_forest) cudaFree(const_cast<unsigned char*>(m->block_forest));
     if (m->tblock_forest) cudaFree(const_cast<unsigned char*>(m->tblock_forest));
     delete m->h_topt;
+    delete m->h_toptn;
     delete m->h_topw;
     delete m->h_topc;
     delete m;
@@ -536,8 +541,9 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bp_bytes = (size_t)(W + 2 * pad) * m->d.A * sizeof(float);
     const size_t smem_max = 227 * 1024;
-    if (m->d.rank_ok && m->use_rank && (m->variant == 3 || m->variant == 5) && m->h_topt) {
-        const bool blockv = (m->variant == 5);
+    if (m->d.rank_ok && m->use_rank && (m->variant == 3 || m->variant == 5 || m->variant == 6) && m->h_topt) {
+        const bool blockv = (m->variant >= 5);
+        const bool narrow_top = (m->variant == 6);
         const unsigned char* timgp = blockv ? m->tblock_forest : m->tile_forest;
         const size_t timgb = blockv ? m->tblock_forest_bytes : m->tile_forest_bytes;
         // tile variant: K4a rank transform into a stream-ordered scratch buffer, K4b tile kernel
@@ -560,14 +566,18 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
             const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count());
 #define CALLT(AT)                                                                                                              \
     do {                                                                                                                       \
-        if (blockv) {                                                                                                          \
-            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gbt_smooth_tile_kernel<AT, true><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
-                                                                             Lseg, proba_dev, label_dev);                     \
+        if (narrow_top) {                                                                                                      \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, true, GbtTopC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_tile_kernel<AT, true, GbtTopC><<<grid, RK_THREADS, smem, st>>>(*m->h_toptn, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
+                                                                                      Lseg, proba_dev, label_dev);            \
+        } else if (blockv) {                                                                                                   \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, true, GbtTopW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_tile_kernel<AT, true, GbtTopW><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
+                                                                                      Lseg, proba_dev, label_dev);            \
         } else {                                                                                                               \
-            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gbt_smooth_tile_kernel<AT, false><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
-                                                                              Lseg, proba_dev, label_dev);                    \
+            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, false, GbtTopW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gbt_smooth_tile_kernel<AT, false, GbtTopW><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
+                                                                                       Lseg, proba_dev, label_dev);           \
         }                                                                                                                      \
     } while (0)
             GBT_DISPATCH_A(m->d.A, CALLT)
@@ -582,7 +592,7 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
         // per haplotype when the chromosome fits shared memory; (G, Lseg) chosen for the best fit of
         // rows to the 1024 threads.
         const size_t slot_bytes = (size_t)m->d.astride * 4;
-        const int var = (m->variant == 3 || m->variant == 5) ? (m->h_topc ? 1 : 0) : m->variant;  // tile variants not applicable here
+        const int var = (m->variant == 3 || m->variant >= 5) ? (m->h_topc ? 1 : 0) : m->variant;  // tile variants not applicable here
         const size_t img_bytes = (var == 2) ? m->wide_forest_bytes : (var == 4) ? m->block_forest_bytes : m->rank_forest_bytes;
         const unsigned char* img = (var == 2) ? m->wide_forest : (var == 4) ? m->block_forest : m->rank_forest;
         const size_t room = smem_max - img_bytes - 16;
@@ -652,12 +662,12 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
 
 int gnx_gbt_set_kernel(gnx_gbt_t* m, int which) {
     GNX_REQUIRE(m != nullptr, "gnx_gbt_set_kernel: NULL model");
-    GNX_REQUIRE(which == 0 || which == 1 || (which >= 10 && which <= 15), "gnx_gbt_set_kernel: unknown kernel %d", which);
+    GNX_REQUIRE(which == 0 || which == 1 || (which >= 10 && which <= 16), "gnx_gbt_set_kernel: unknown kernel %d", which);
     if (which >= 10) {  // rank-form flavour: 10 narrow nodes, 11 narrow + parameter-bank tops, 12 wide nodes
         const int v = which - 10;
         m->use_rank = 1;
         if (!m->d.rank_ok) return 0;  // not a rank-form forest: the generic kernel runs whatever the flavour
-        GNX_REQUIRE(v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt) || (v == 4 && m->block_forest) || (v == 5 && m->tblock_forest), "gnx_gbt_set_kernel: flavour %d not available for this forest", v);
+        GNX_REQUIRE(v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt) || (v == 4 && m->block_forest) || ((v == 5 || v == 6) && m->tblock_forest), "gnx_gbt_set_kernel: flavour %d not available for this forest", v);
         m->variant = v;
         m->use_rank = 1;
         return 0;

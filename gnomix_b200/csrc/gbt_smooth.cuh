@@ -326,6 +326,39 @@ __device__ __forceinline__ void gbt_rank_walk_to(int A, uint32_t row, const GbtT
     }
 }
 
+// The same walk with one-word tree tops (k << 16 | feat) in the parameter bank: half the constant-cache footprint.
+template <int AT>
+__device__ __forceinline__ void gbt_rank_walk_to(int A, uint32_t row, const GbtTopC& top, const uint32_t* __restrict__ blk,
+                                                 const float* __restrict__ lv, int rounds, float* psum) {
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+#pragma unroll
+    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+    int tbase = 0;
+    const unsigned char* bb = reinterpret_cast<const unsigned char*>(blk);
+    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+        for (int c = 0; c < AMAX; c++) {
+            if (c < A) {
+                const uint32_t t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
+                const bool b0 = gnx_lds_u32(row + ((t0 & 0xffffu) << 7)) > t0;
+                const uint32_t n1 = b0 ? t2 : t1;
+                uint32_t o = b0 ? 32u : 0u;
+                gnx_add_if_gt(o, gnx_lds_u32(row + ((n1 & 0xffffu) << 7)), n1, 16u);
+                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + o);
+                gnx_add_if_gt(o, gnx_lds_u32(row + ((n2 & 0xffffu) << 7)), n2, 8u);
+                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + 4 + o);
+                gnx_add_if_gt(o, gnx_lds_u32(row + ((n3 & 0xffffu) << 7)), n3, 4u);
+                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
+            }
+        }
+        tbase += 3 * A;
+        bb += RK_BLOCK * 4 * A;
+        lvb += RK_LEAVES * 4 * A;
+    }
+}
+
 // Wide-node variant (default of gbt_smooth): every node is two words { k << 16, byte offset of the
 // feature in a row }, so the feature address is one add (no mask) and the walk carries BYTE offsets
 // into the level-2 / level-3 / leaf arrays (select + shift-add per level instead of index arithmetic).
@@ -396,6 +429,7 @@ struct gnx_gbt {
     gnx::GbtTopW* h_topw;    // wide-node variant: top nodes (parameter bank) ...
     const unsigned char* wide_forest;  // ... and lower uint2 [T][12] | leaves [T][16] (shared-memory image)
     size_t wide_forest_bytes;
+    gnx::GbtTopC* h_toptn;   // tile variants with one-word tops (k << 16 | feat): gnx_gbt_set_kernel 16
     gnx::GbtTopW* h_topt;    // tile variant: top nodes { k << 16, feat * 128 } (parameter bank) ...
     const unsigned char* tile_forest;  // ... and lower u32 [T][12] | leaves [T][16], node = (k << 16) | feat
     size_t tile_forest_bytes;

@@ -99,12 +99,13 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
 void gnx_gbt_model_destroy(gnx_gbt_t* m);
 /* kernel selector: 0 = rank-form kernel (default; depth <= 4 forests, falls back by itself
  *                      otherwise), 1 = generic float traversal (cross-check; same results);
- *                  10 .. 15 = rank-form kernel with a given layout: 10 one-word nodes / 11 one-word
+ *                  10 .. 16 = rank-form kernel with a given layout: 10 one-word nodes / 11 one-word
  *                      nodes + tree tops in the parameter bank / 12 two-word nodes / 13 lane-
  *                      interleaved haplotype tiles behind a separate rank pass / 14 block layout
  *                      with one accumulating byte offset per walk (the default) / 15 tiles + block
- *                      layout.  Same results; measurements in profiles/README.md.
- * Environment GNX_GBT_VARIANT=0..5 picks the layout at model-create time (profiling). */
+ *                      layout, two-word tree tops / 16 the same with one-word tree tops (fastest
+ *                      measured, 3 % ahead of 14).  Same results; measurements in profiles/README.md.
+ * Environment GNX_GBT_VARIANT=0..6 picks the layout at model-create time (profiling). */
 int gnx_gbt_set_kernel(gnx_gbt_t* m, int which);
 /* proba_dev [N,W,A] float32 and label_dev [N,W] int32; either may be NULL */
 int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, float* proba_dev,
