@@ -74,9 +74,8 @@ gbt_smooth_rank_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
         uint4* dst = reinterpret_cast<uint4*>(smem);
         for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    // VAR 2 (wide): lower uint2 [T][12] | leaves [T][16];  VAR 0/1: lower u32 [T][12] | leaves | top uint4 [T]
-    // VAR 4 (accumulating offset): block u32 [T][16] | leaves [T][16]
-    constexpr int LOWER_B = (VAR == 2) ? RK_LOWER * 8 : (VAR == 4) ? RK_BLOCK * 4 : RK_LOWER * 4;
+    // VAR 0: lower u32 [T][12] | leaves [T][16] | top uint4 [T];  VAR 4 (accumulating offset): block u32 [T][16] | leaves [T][16]
+    constexpr int LOWER_B = (VAR == 4) ? RK_BLOCK * 4 : RK_LOWER * 4;
     const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
     const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * LOWER_B);
     const uint4* top_s = reinterpret_cast<const uint4*>(smem + (size_t)m.T * (RK_LOWER + RK_LEAVES) * 4);
@@ -137,115 +136,12 @@ gbt_smooth_rank_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
                 gbt_eval_row<AT>(m, m.nodes, m.leaves, reinterpret_cast<const float*>(rk) + h * unit_words + wl * A, psum);
             } else {
                 const unsigned char* row = reinterpret_cast<const unsigned char*>(rk + h * unit_words + wl * ast);
-                if constexpr (VAR == 2)
-                    gbt_rank_walk_w<AT>(A, row, topc, reinterpret_cast<const unsigned char*>(lower_s),
-                                        reinterpret_cast<const unsigned char*>(leaves_s), rounds, psum);
-                else if constexpr (VAR == 4)
+                if constexpr (VAR == 4)
                     gbt_rank_walk_o<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
-                else if constexpr (VAR == 1)
-                    gbt_rank_walk_c<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
                 else
                     gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
             }
             gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
-        }
-    }
-}
-
-// ---------------------------------------------------------------- tile variant (two kernels)
-// K4a: exact rank transform of the base probabilities, B f32 [n] -> R u16 [n]; NaN -> 0xFFFF.
-__global__ void __launch_bounds__(512)
-gbt_rank_u16_kernel(const float* __restrict__ thr, int K, int table_in_smem, const float* __restrict__ B, int64_t count,
-                    uint16_t* __restrict__ R) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const float* tab = thr;
-    if (table_in_smem) {
-        float* t = reinterpret_cast<float*>(smem);
-        for (int i = threadIdx.x; i < K; i += blockDim.x) t[i] = __ldg(thr + i);
-        __syncthreads();
-        tab = t;
-    }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        const float x = __ldg(B + i);
-        int lo = 0, hi = K;  // #{j : tab[j] <= x}
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (tab[mid] <= x) lo = mid + 1; else hi = mid;
-        }
-        R[i] = (x != x) ? (uint16_t)0xFFFFu : (uint16_t)lo;
-    }
-}
-
-// K4b: tile = 32 haplotypes (lane = haplotype) x Lseg windows (warp = window); the rank tile is
-// lane-interleaved in shared memory (see gbt_rank_walk_t), the forest sits next to it.
-template <int AT, bool BLOCK, typename TOPT>
-__global__ void __launch_bounds__(RK_THREADS, 1)
-gbt_smooth_tile_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsigned char* __restrict__ forest_img,
-                       size_t forest_bytes, const uint16_t* __restrict__ R, const float* __restrict__ B, int64_t N, int W,
-                       int nseg, int Lseg, float* __restrict__ proba, int32_t* __restrict__ label) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int A = AT ? AT : m.A;
-    constexpr int AMAX = AT ? AT : GBT_MAX_A;
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(forest_img);
-        uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
-    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * (BLOCK ? RK_BLOCK : RK_LOWER) * 4);
-    uint32_t* tile = reinterpret_cast<uint32_t*>(smem + forest_bytes);
-    const int pad = (m.S + 1) / 2;
-    const int Lslots = Lseg + m.S - 1;
-    const int rounds = m.T / A;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t nhb = (N + 31) / 32;
-    for (int64_t t = blockIdx.x; t < nhb * nseg; t += gridDim.x) {
-        const int64_t hb = t / nseg;
-        const int sg = (int)(t - hb * nseg);
-        const int64_t n = hb * 32 + lane;
-        const int w0 = sg * Lseg;
-        __syncthreads();
-        int saw_nan = 0;
-        for (int e = warp; e < Lslots * A; e += RK_THREADS / 32) {
-            const int jl = e / A, a = e - jl * A;
-            const int j = w0 + jl;
-            uint32_t r = 0;
-            if (n < N && j < W + m.S - 1) r = __ldg(R + (n * W + spad_to_orig(j, W, pad)) * A + a);
-            saw_nan |= (r == 0xFFFFu);
-            tile[e * 32 + lane] = r << 16;
-        }
-        const int slow = __syncthreads_or(saw_nan);
-        if (slow) {
-            // NaN inputs follow each node's default child: generic float traversal, one haplotype of the
-            // tile at a time, its padded float row staged where the rank tile was
-            float* bp = reinterpret_cast<float*>(tile);
-            for (int h = 0; h < 32; h++) {
-                const int64_t nh = hb * 32 + h;
-                if (nh >= N) break;
-                __syncthreads();
-                for (int e = threadIdx.x; e < Lslots * A; e += blockDim.x) {
-                    const int jl = e / A, a = e - jl * A;
-                    const int j = w0 + jl;
-                    bp[e] = (j < W + m.S - 1) ? __ldg(B + (nh * W + spad_to_orig(j, W, pad)) * A + a) : 0.f;
-                }
-                __syncthreads();
-                for (int wl = threadIdx.x; wl < Lseg && w0 + wl < W; wl += blockDim.x) {
-                    float psum[AMAX];
-                    gbt_eval_row<AT>(m, m.nodes, m.leaves, bp + (size_t)wl * A, psum);
-                    const int64_t row = nh * W + w0 + wl;
-                    gbt_finish<AT>(m, psum, proba ? proba + row * A : nullptr, label ? label + row : nullptr);
-                }
-            }
-            continue;
-        }
-        for (int wl = warp; wl < Lseg; wl += RK_THREADS / 32) {
-            const int w = w0 + wl;
-            if (w >= W) break;
-            const uint32_t row = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)(wl * A * 128 + lane * 4);
-            float psum[AMAX];
-            if constexpr (BLOCK) gbt_rank_walk_to<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
-            else if constexpr (std::is_same<TOPT, GbtTopW>::value) gbt_rank_walk_t<AT>(A, row, topc, lower_s, leaves_s, rounds, psum);
-            if (n < N) gbt_finish<AT>(m, psum, proba ? proba + (n * W + w) * A : nullptr, label ? label + n * W + w : nullptr);
         }
     }
 }
@@ -372,28 +268,14 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
             memcpy(rleaves + (size_t)t * RK_LEAVES, leaves.data() + (size_t)t * n_leaf, sizeof(float) * RK_LEAVES);
         }
     }
-    // wide image: lower uint2 [T][12] | leaves [T][16]
-    std::vector<uint32_t> wimg;
-    if (rank_ok) {
-        wimg.assign((size_t)n_trees * (2 * RK_LOWER + RK_LEAVES), 0u);
-        const uint32_t* lower = rimg.data();
-        for (size_t i = 0; i < (size_t)n_trees * RK_LOWER; i++) {
-            wimg[2 * i] = lower[i] & 0xffff0000u;
-            wimg[2 * i + 1] = lower[i] & 0xffffu;
-        }
-        memcpy(wimg.data() + (size_t)n_trees * 2 * RK_LOWER, rimg.data() + (size_t)n_trees * RK_LOWER,
-               sizeof(uint32_t) * (size_t)n_trees * RK_LEAVES);
-    }
-    const size_t wb = (wimg.size() * 4 + 15) & ~size_t(15);
     const size_t rb = rimg.size() * 4, tb = ((size_t)K * 4 + 15) & ~size_t(15);
     char* blob = nullptr;
-    GNX_CUDA(cudaMalloc((void**)&blob, forest + 256 + rb + tb + wb + 16));
+    GNX_CUDA(cudaMalloc((void**)&blob, forest + 256 + rb + tb + 16));
     bool ok = cudaMemcpy(blob, nodes.data(), nb, cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(blob + nb, leaves.data(), lb, cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(blob + forest, base_margin, sizeof(float) * A, cudaMemcpyHostToDevice) == cudaSuccess;
     if (rb) ok &= cudaMemcpy(blob + forest + 256, rimg.data(), rb, cudaMemcpyHostToDevice) == cudaSuccess;
     if (K) ok &= cudaMemcpy(blob + forest + 256 + rb, tab.data(), (size_t)K * 4, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (wb) ok &= cudaMemcpy(blob + forest + 256 + rb + tb, wimg.data(), wimg.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         cudaFree(blob);
         set_error("gnx_gbt_model_create: H2D copy failed");
@@ -412,94 +294,72 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->rank_forest = reinterpret_cast<const unsigned char*>(blob + forest + 256);
     m->use_rank = 1;
     m->h_topc = nullptr;
-    if (rank_ok && n_trees <= GBT_TOPC_MAX_T) {
-        m->h_topc = new GbtTopC();
-        const uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
-        for (int t = 0; t < n_trees; t++)
-            for (int k = 0; k < 3; k++) m->h_topc->w[3 * t + k] = top[(size_t)t * 4 + k];
-    }
-    // tile image: the narrow image with the feature index in the low half of every node word
-    m->h_topt = nullptr;
-    m->h_toptn = nullptr;
+    m->h_tiletop = nullptr;
+    m->h_tiletop3 = nullptr;
+    m->tile_top_words = 4;
     m->tile_forest = nullptr;
     m->tile_forest_bytes = 0;
-    m->tblock_forest = nullptr;
-    m->tblock_forest_bytes = 0;
-    if (rank_ok && n_trees <= GBT_TOPW_MAX_T && K <= 65534 && F <= 65535) {
-        std::vector<uint32_t> timg((size_t)n_trees * (RK_LOWER + RK_LEAVES), 0u);
-        m->h_topt = new GbtTopW();
-        m->h_toptn = new GbtTopC();
-        auto conv = [&](uint32_t word) -> uint32_t {  // (k << 16 | byte offset in a row) -> (k << 16 | feature index)
-            const uint32_t off = (word & 0xffffu) / 4u, slot = off / (uint32_t)astride, a = off % (uint32_t)astride;
-            return (word & 0xffff0000u) | (slot * (uint32_t)A + a);
-        };
-        const uint32_t* lower = rimg.data();
-        const uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
-        for (size_t i = 0; i < (size_t)n_trees * RK_LOWER; i++) timg[i] = conv(lower[i]);
-        memcpy(timg.data() + (size_t)n_trees * RK_LOWER, rimg.data() + (size_t)n_trees * RK_LOWER, sizeof(uint32_t) * (size_t)n_trees * RK_LEAVES);
-        for (int t = 0; t < n_trees; t++)
-            for (int k = 0; k < 3; k++) {
-                const uint32_t wd = conv(top[(size_t)t * 4 + k]);
-                m->h_topt->w[3 * t + k] = make_uint2(wd & 0xffff0000u, (wd & 0xffffu) * 128u);
-                m->h_toptn->w[3 * t + k] = wd;
-            }
-        void* d_t = nullptr;
-        if (cudaMalloc(&d_t, timg.size() * 4) != cudaSuccess || cudaMemcpy(d_t, timg.data(), timg.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
-            set_error("gnx_gbt_model_create: tile image allocation failed");
-            return 1;
-        }
-        m->tile_forest = static_cast<const unsigned char*>(d_t);
-        m->tile_forest_bytes = timg.size() * 4;
-        std::vector<uint32_t> tb((size_t)n_trees * (RK_BLOCK + RK_LEAVES), 0u);
-        for (int t = 0; t < n_trees; t++) {
-            for (int i2 = 0; i2 < 4; i2++) tb[(size_t)t * RK_BLOCK + 4 * i2] = timg[(size_t)t * RK_LOWER + i2];
-            for (int i3 = 0; i3 < 8; i3++) tb[(size_t)t * RK_BLOCK + 2 * i3 + 1] = timg[(size_t)t * RK_LOWER + 4 + i3];
-        }
-        memcpy(tb.data() + (size_t)n_trees * RK_BLOCK, timg.data() + (size_t)n_trees * RK_LOWER, sizeof(uint32_t) * (size_t)n_trees * RK_LEAVES);
-        void* d_tb = nullptr;
-        if (cudaMalloc(&d_tb, tb.size() * 4) != cudaSuccess || cudaMemcpy(d_tb, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
-            set_error("gnx_gbt_model_create: tile block image allocation failed");
-            return 1;
-        }
-        m->tblock_forest = static_cast<const unsigned char*>(d_tb);
-        m->tblock_forest_bytes = tb.size() * 4;
-    }
-    // block image (accumulating-offset variant): per tree 16 words -- level-2 node i2 at word 4 * i2, level-3 node
-    // i3 at word 2 * i3 + 1 -- then the leaves
     m->block_forest = nullptr;
     m->block_forest_bytes = 0;
+    auto fail = [&](const char* what) {
+        set_error("gnx_gbt_model_create: %s", what);
+        gnx_gbt_model_destroy(m);
+        return 1;
+    };
     if (rank_ok && n_trees <= GBT_TOPC_MAX_T) {
-        std::vector<uint32_t> bimg((size_t)n_trees * (RK_BLOCK + RK_LEAVES), 0u);
         const uint32_t* lower = rimg.data();
+        const uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
+        m->h_topc = new GbtTopC();
+        for (int t = 0; t < n_trees; t++)
+            for (int k = 0; k < 3; k++) m->h_topc->w[3 * t + k] = top[(size_t)t * 4 + k];
+        // block image (accumulating-offset walk of the row kernel): per tree 16 words -- level-2 node i2 at word
+        // 4 * i2, level-3 node i3 at word 2 * i3 + 1 -- then the leaves of all trees
+        std::vector<uint32_t> bimg((size_t)n_trees * (RK_BLOCK + RK_LEAVES), 0u);
         for (int t = 0; t < n_trees; t++) {
             for (int i2 = 0; i2 < 4; i2++) bimg[(size_t)t * RK_BLOCK + 4 * i2] = lower[(size_t)t * RK_LOWER + i2];
             for (int i3 = 0; i3 < 8; i3++) bimg[(size_t)t * RK_BLOCK + 2 * i3 + 1] = lower[(size_t)t * RK_LOWER + 4 + i3];
         }
         memcpy(bimg.data() + (size_t)n_trees * RK_BLOCK, rimg.data() + (size_t)n_trees * RK_LOWER, sizeof(uint32_t) * (size_t)n_trees * RK_LEAVES);
         void* d_b = nullptr;
-        if (cudaMalloc(&d_b, bimg.size() * 4) != cudaSuccess || cudaMemcpy(d_b, bimg.data(), bimg.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
-            set_error("gnx_gbt_model_create: block image allocation failed");
-            return 1;
-        }
+        if (cudaMalloc(&d_b, bimg.size() * 4) != cudaSuccess) return fail("block image allocation failed");
         m->block_forest = static_cast<const unsigned char*>(d_b);
         m->block_forest_bytes = bimg.size() * 4;
+        if (cudaMemcpy(d_b, bimg.data(), bimg.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("block image copy failed");
+        // tile image (gbt_tile.cu): node word (k << 17) | (feature << 7), so `rank << 17 > word` is the split test and
+        // `word & 0x1ff80` the byte offset of the feature in a lane-interleaved tile; one 128-byte record per tree:
+        // the same 16-word block, then its 16 leaves
+        if (K <= GBT_TILE_MAX_K && F <= GBT_TILE_MAX_F && n_trees <= GBT_TILE_MAX_T) {
+            auto conv = [&](uint32_t word) -> uint32_t {  // (k << 16 | byte offset in a rank row) -> tile word
+                const uint32_t k = word >> 16, off = (word & 0xffffu) / 4u, slot = off / (uint32_t)astride, a = off % (uint32_t)astride;
+                const uint32_t kk = (k == 0xFFFFu) ? (uint32_t)GBT_TILE_MAX_K : k;   // always-left filler: no rank exceeds it
+                return (kk << 17) | ((slot * (uint32_t)A + a) << 7);
+            };
+            std::vector<uint32_t> timg((size_t)n_trees * 32, 0u);
+            for (int t = 0; t < n_trees; t++) {
+                for (int i2 = 0; i2 < 4; i2++) timg[(size_t)t * 32 + 4 * i2] = conv(lower[(size_t)t * RK_LOWER + i2]);
+                for (int i3 = 0; i3 < 8; i3++) timg[(size_t)t * 32 + 2 * i3 + 1] = conv(lower[(size_t)t * RK_LOWER + 4 + i3]);
+                memcpy(timg.data() + (size_t)t * 32 + 16, rimg.data() + (size_t)n_trees * RK_LOWER + (size_t)t * RK_LEAVES, sizeof(uint32_t) * RK_LEAVES);
+            }
+            m->h_tiletop = new GbtTileTop();
+            m->h_tiletop3 = new GbtTopC();
+            for (int t = 0; t < n_trees; t++) {
+                const uint32_t t0 = conv(top[(size_t)t * 4]);
+                m->h_tiletop->q[t] = make_uint4(t0, conv(top[(size_t)t * 4 + 1]), conv(top[(size_t)t * 4 + 2]), t0 & 0x1ff80u);
+                for (int k = 0; k < 3; k++) m->h_tiletop3->w[3 * t + k] = conv(top[(size_t)t * 4 + k]);
+            }
+            const char* tw = getenv("GNX_GBT_TOPW");
+            m->tile_top_words = (tw && atoi(tw) == 3) ? 3 : 4;
+            void* d_t = nullptr;
+            if (cudaMalloc(&d_t, timg.size() * 4) != cudaSuccess) return fail("tile image allocation failed");
+            m->tile_forest = static_cast<const unsigned char*>(d_t);
+            m->tile_forest_bytes = timg.size() * 4;
+            if (cudaMemcpy(d_t, timg.data(), timg.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("tile image copy failed");
+        }
     }
-    m->h_topw = nullptr;
-    m->wide_forest = reinterpret_cast<const unsigned char*>(blob + forest + 256 + rb + tb);
-    m->wide_forest_bytes = wb;
-    if (rank_ok && n_trees <= GBT_TOPW_MAX_T) {
-        m->h_topw = new GbtTopW();
-        const uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
-        for (int t = 0; t < n_trees; t++)
-            for (int k = 0; k < 3; k++) m->h_topw->w[3 * t + k] = make_uint2(top[(size_t)t * 4 + k] & 0xffff0000u, top[(size_t)t * 4 + k] & 0xffffu);
-    }
-    // measured on B200 (chr1 x 20 000 haplotypes, scripts/k4_probe.py): accumulating-offset block layout 22.7 ms,
-    // one-word nodes + byte-offset walk 23.7 ms, two-word nodes 25.4 ms (LDS.64 costs two shared-memory wavefronts
-    // and the kernel is wavefront / issue co-limited), lane-interleaved tiles 25.7 ms, tiles + block layout 26.8 ms
-    m->variant = (m->block_forest && m->h_topc) ? 4 : (m->h_topc ? 1 : 0);
+    m->variant = -1;  // chosen per call: tile kernel for batches of haplotypes, row kernel otherwise
     if (const char* e = getenv("GNX_GBT_VARIANT")) {  // profiling / cross-check switch
         const int v = atoi(e);
-        if (v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt) || (v == 4 && m->block_forest) || ((v == 5 || v == 6) && m->tblock_forest)) m->variant = v;
+        if (v == 0 || (v == 4 && m->block_forest) || (v == 6 && m->tile_forest)) m->variant = v;
     }
     *out = m;
     return 0;
@@ -510,10 +370,8 @@ void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->tile_forest) cudaFree(const_cast<unsigned char*>(m->tile_forest));
     if (m->block_forest) cudaFree(const_cast<unsigned char*>(m->block_forest));
-    if (m->tblock_forest) cudaFree(const_cast<unsigned char*>(m->tblock_forest));
-    delete m->h_topt;
-    delete m->h_toptn;
-    delete m->h_topw;
+    delete m->h_tiletop;
+    delete m->h_tiletop3;
     delete m->h_topc;
     delete m;
 }
@@ -541,60 +399,20 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bp_bytes = (size_t)(W + 2 * pad) * m->d.A * sizeof(float);
     const size_t smem_max = 227 * 1024;
-    if (m->d.rank_ok && m->use_rank && (m->variant == 3 || m->variant == 5 || m->variant == 6) && m->h_topt) {
-        const bool blockv = (m->variant >= 5);
-        const bool narrow_top = (m->variant == 6);
-        const unsigned char* timgp = blockv ? m->tblock_forest : m->tile_forest;
-        const size_t timgb = blockv ? m->tblock_forest_bytes : m->tile_forest_bytes;
-        // tile variant: K4a rank transform into a stream-ordered scratch buffer, K4b tile kernel
-        const size_t slot_bytes = (size_t)m->d.A * 128;
-        const size_t room = smem_max - timgb - 16;
-        const int Lmax = (int)std::min<int64_t>((int64_t)(room / slot_bytes) - (m->d.S - 1), 2 * (RK_THREADS / 32));
-        if (Lmax >= 32 || Lmax >= W) {
-            const int nseg = (int)ceil_div(W, std::min(Lmax, W));
-            const int Lseg = (int)ceil_div(W, nseg);
-            const size_t smem = timgb + (size_t)(Lseg + m->d.S - 1) * slot_bytes + 16;
-            const int64_t count = N * (int64_t)W * m->d.A;
-            uint16_t* R = nullptr;
-            GNX_CUDA(cudaMallocAsync((void**)&R, (size_t)count * sizeof(uint16_t), st));
-            const int in_smem = (size_t)m->d.K * 4 <= 160 * 1024;
-            const size_t rsm = in_smem ? (size_t)m->d.K * 4 : 0;
-            GNX_CUDA(cudaFuncSetAttribute(gbt_rank_u16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
-            gbt_rank_u16_kernel<<<(int)std::min<int64_t>(ceil_div(count, 512), (int64_t)sm_count() * 4), 512, rsm, st>>>(
-                m->d.thr_table, m->d.K, in_smem, B_dev, count, R);
-            const int64_t tiles = ceil_div(N, 32) * nseg;
-            const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count());
-#define CALLT(AT)                                                                                                              \
-    do {                                                                                                                       \
-        if (narrow_top) {                                                                                                      \
-            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, true, GbtTopC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gbt_smooth_tile_kernel<AT, true, GbtTopC><<<grid, RK_THREADS, smem, st>>>(*m->h_toptn, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
-                                                                                      Lseg, proba_dev, label_dev);            \
-        } else if (blockv) {                                                                                                   \
-            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, true, GbtTopW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gbt_smooth_tile_kernel<AT, true, GbtTopW><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
-                                                                                      Lseg, proba_dev, label_dev);            \
-        } else {                                                                                                               \
-            GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, false, GbtTopW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gbt_smooth_tile_kernel<AT, false, GbtTopW><<<grid, RK_THREADS, smem, st>>>(*m->h_topt, m->d, timgp, timgb, R, B_dev, N, W, nseg, \
-                                                                                       Lseg, proba_dev, label_dev);           \
-        }                                                                                                                      \
-    } while (0)
-            GBT_DISPATCH_A(m->d.A, CALLT)
-#undef CALLT
-            GNX_CUDA(cudaGetLastError());
-            GNX_CUDA(cudaFreeAsync(R, st));
-            return 0;
-        }
+    // tile kernel (gbt_tile.cu): lanes = 32 haplotypes, so it wants a batch; single individuals (and the labels
+    // pass of gnofix on few rows) take the row kernel, whose lanes are windows of one haplotype
+    if (m->d.rank_ok && m->use_rank && m->tile_forest && (m->variant == 6 || (m->variant < 0 && N >= GBT_TILE_MIN_N))) {
+        const int rc = gbt_tile_smooth(m, B_dev, N, W, proba_dev, label_dev, st);
+        if (rc >= 0) return rc;
     }
     if (m->d.rank_ok && m->use_rank) {
         // fast path: units of (haplotype, segment of Lseg windows), G units per CTA pass.  One segment
         // per haplotype when the chromosome fits shared memory; (G, Lseg) chosen for the best fit of
         // rows to the 1024 threads.
         const size_t slot_bytes = (size_t)m->d.astride * 4;
-        const int var = (m->variant == 3 || m->variant >= 5) ? (m->h_topc ? 1 : 0) : m->variant;  // tile variants not applicable here
-        const size_t img_bytes = (var == 2) ? m->wide_forest_bytes : (var == 4) ? m->block_forest_bytes : m->rank_forest_bytes;
-        const unsigned char* img = (var == 2) ? m->wide_forest : (var == 4) ? m->block_forest : m->rank_forest;
+        const int var = (m->variant == 0 || !m->block_forest) ? 0 : 4;
+        const size_t img_bytes = (var == 4) ? m->block_forest_bytes : m->rank_forest_bytes;
+        const unsigned char* img = (var == 4) ? m->block_forest : m->rank_forest;
         const size_t room = smem_max - img_bytes - 16;
         int bestG = 0, bestL = 0;
         double best_eff = 0.0;
@@ -624,10 +442,6 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
     do {                                                           \
         if (var == 4) {                                            \
             LAUNCHR(AT, 4, GbtTopC, *m->h_topc);                   \
-        } else if (var == 2) {                                     \
-            LAUNCHR(AT, 2, GbtTopW, *m->h_topw);                   \
-        } else if (var == 1) {                                     \
-            LAUNCHR(AT, 1, GbtTopC, *m->h_topc);                   \
         } else {                                                   \
             static const GbtTopC none{};                           \
             LAUNCHR(AT, 0, GbtTopC, none);                         \
@@ -662,17 +476,14 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
 
 int gnx_gbt_set_kernel(gnx_gbt_t* m, int which) {
     GNX_REQUIRE(m != nullptr, "gnx_gbt_set_kernel: NULL model");
-    GNX_REQUIRE(which == 0 || which == 1 || (which >= 10 && which <= 16), "gnx_gbt_set_kernel: unknown kernel %d", which);
-    if (which >= 10) {  // rank-form flavour: 10 narrow nodes, 11 narrow + parameter-bank tops, 12 wide nodes
+    GNX_REQUIRE(which == 0 || which == 1 || which == 10 || which == 14 || which == 16, "gnx_gbt_set_kernel: unknown kernel %d", which);
+    m->use_rank = (which != 1);
+    if (which == 0) m->variant = -1;
+    if (which >= 10 && m->d.rank_ok) {  // not a rank-form forest: the generic kernel runs whatever is asked
         const int v = which - 10;
-        m->use_rank = 1;
-        if (!m->d.rank_ok) return 0;  // not a rank-form forest: the generic kernel runs whatever the flavour
-        GNX_REQUIRE(v == 0 || (v == 1 && m->h_topc) || (v == 2 && m->h_topw) || (v == 3 && m->h_topt) || (v == 4 && m->block_forest) || ((v == 5 || v == 6) && m->tblock_forest), "gnx_gbt_set_kernel: flavour %d not available for this forest", v);
+        GNX_REQUIRE(v == 0 || (v == 4 && m->block_forest) || (v == 6 && m->tile_forest), "gnx_gbt_set_kernel: kernel %d not available for this forest", which);
         m->variant = v;
-        m->use_rank = 1;
-        return 0;
     }
-    m->use_rank = (which == 0);
     return 0;
 }
 

@@ -12,6 +12,11 @@ constexpr int GBT_MAX_DEPTH = 8;
 constexpr int RK_THREADS = 1024;
 constexpr int RK_LOWER = 12;   // nodes 3..14 of a depth-4 heap
 constexpr int RK_LEAVES = 16;
+// tile kernel (gbt_tile.cu): node word = (k << 17) | (feature << 7)
+constexpr int GBT_TILE_MAX_K = 32767;   // threshold indices (and ranks) must fit 15 bits
+constexpr int GBT_TILE_MAX_F = 1023;    // feature << 7 must stay below bit 17
+constexpr int GBT_TILE_MAX_T = 1792;    // tree tops travel in the kernel parameter bank (28 KB of the 32 KB)
+constexpr int GBT_TILE_MIN_N = 24;      // below this many haplotypes the row kernel is used (lanes = haplotypes here)
 
 // Heap-ordered complete forest.  Tree t: (2^D - 1) split nodes then 2^D leaves.
 // Shallower subtrees are padded with always-left splits whose both children carry
@@ -154,52 +159,19 @@ __device__ __forceinline__ void gbt_rank_walk(int A, const unsigned char* __rest
     }
 }
 
-// Same walk with the top three nodes of every tree read from the kernel parameter bank
-// (warp-uniform index -> constant-cache broadcast instead of a shared-memory wavefront).
+// Tree tops in the kernel parameter bank (warp-uniform index -> constant-cache broadcast instead of a
+// shared-memory wavefront): one word per node, three per tree.
 constexpr int GBT_TOPC_MAX_T = 2048;
 struct GbtTopC {
     uint32_t w[3 * GBT_TOPC_MAX_T];
 };
 
-template <int AT>
-__device__ __forceinline__ void gbt_rank_walk_c(int A, const unsigned char* __restrict__ row, const GbtTopC& top,
-                                                const uint32_t* __restrict__ lw, const float* __restrict__ lv, int rounds,
-                                                float* psum) {
-    constexpr int AMAX = AT ? AT : GBT_MAX_A;
-#pragma unroll
-    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
-    int tbase = 0;
-    const unsigned char* lwb = reinterpret_cast<const unsigned char*>(lw);
-    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
-#pragma unroll 1
-    for (int rd = 0; rd < rounds; rd++) {
-#pragma unroll
-        for (int c = 0; c < AMAX; c++) {
-            if (c < A) {
-                // the walk carries BYTE offsets into the level-2 / level-3 / leaf arrays: one select and
-                // one shift-add per level instead of index arithmetic
-                const uint32_t t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
-                const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (t0 & 0xffffu));
-                const bool b0 = x0 > t0;
-                const uint32_t n1 = b0 ? t2 : t1;
-                const uint32_t x1 = *reinterpret_cast<const uint32_t*>(row + (n1 & 0xffffu));
-                uint32_t o = (b0 ? 8u : 0u) + ((x1 > n1) ? 4u : 0u);
-                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(lwb + c * (RK_LOWER * 4) + o);
-                const uint32_t x2 = *reinterpret_cast<const uint32_t*>(row + (n2 & 0xffffu));
-                o = 2u * o + ((x2 > n2) ? 4u : 0u);
-                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(lwb + c * (RK_LOWER * 4) + 16 + o);
-                const uint32_t x3 = *reinterpret_cast<const uint32_t*>(row + (n3 & 0xffffu));
-                o = 2u * o + ((x3 > n3) ? 4u : 0u);
-                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
-            }
-        }
-        tbase += 3 * A;
-        lwb += RK_LOWER * 4 * A;
-        lvb += RK_LEAVES * 4 * A;
-    }
-}
+// Tile kernel: per tree { node 0, node 1, node 2, node 0's feature offset } in tile node words, one 16-byte load.
+struct alignas(16) GbtTileTop {
+    uint4 q[GBT_TILE_MAX_T];
+};
 
-// Accumulating-offset variant (gnx_gbt_set_kernel 14): nodes 3..14 of a tree sit in one 64-byte block laid out so
+// Accumulating-offset walk of the row kernel (gnx_gbt_set_kernel 14): nodes 3..14 of a tree sit in one 64-byte block laid out so
 // that a single byte offset o = 32 b0 + 16 b1 + 8 b2 + 4 b3 (b = branch bits) addresses every level: level-2 node at
 // block + (32 b0 + 16 b1), level-3 node at block + (32 b0 + 16 b1 + 8 b2) + 4, leaf at leaves + o.  Each level then
 // costs one compare and one predicated add instead of a select and a shift-add.
@@ -242,162 +214,6 @@ __device__ __forceinline__ void gbt_rank_walk_o(int A, const unsigned char* __re
     }
 }
 
-constexpr int GBT_TOPW_MAX_T = 1024;
-struct GbtTopW {
-    uint2 w[3 * GBT_TOPW_MAX_T];
-};
-
-// Tile variant (gbt_smooth_tile_kernel): the rank tile is lane-interleaved, word ((slot * A + a) * 32 + lane)
-// with lane = haplotype, so a feature load hits bank `lane` whatever node each lane is at (no bank
-// conflicts under divergence).  Top three nodes of every tree: two words { k << 16, feat * 128 } in the
-// kernel parameter bank (no mask, no shared-memory wavefront); nodes 3..14: one word (k << 16) | feat
-// in shared memory (an 8-byte node would cost a second wavefront per load).
-__device__ __forceinline__ uint32_t gnx_lds_u32(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
-
-template <int AT>
-__device__ __forceinline__ void gbt_rank_walk_t(int A, uint32_t row, const GbtTopW& top, const uint32_t* __restrict__ lw,
-                                                const float* __restrict__ lv, int rounds, float* psum) {
-    constexpr int AMAX = AT ? AT : GBT_MAX_A;
-#pragma unroll
-    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
-    int tbase = 0;
-    const unsigned char* lwb = reinterpret_cast<const unsigned char*>(lw);
-    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
-#pragma unroll 1
-    for (int rd = 0; rd < rounds; rd++) {
-#pragma unroll
-        for (int c = 0; c < AMAX; c++) {
-            if (c < A) {
-                const uint2 t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
-                const bool b0 = gnx_lds_u32(row + t0.y) > t0.x;
-                const uint2 n1 = b0 ? t2 : t1;
-                const bool b1 = gnx_lds_u32(row + n1.y) > n1.x;
-                uint32_t o = (b0 ? 8u : 0u) + (b1 ? 4u : 0u);
-                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(lwb + c * (RK_LOWER * 4) + o);
-                const bool b2 = gnx_lds_u32(row + ((n2 & 0xffffu) << 7)) > n2;
-                o = 2u * o + (b2 ? 4u : 0u);
-                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(lwb + c * (RK_LOWER * 4) + 16 + o);
-                const bool b3 = gnx_lds_u32(row + ((n3 & 0xffffu) << 7)) > n3;
-                o = 2u * o + (b3 ? 4u : 0u);
-                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
-            }
-        }
-        tbase += 3 * A;
-        lwb += RK_LOWER * 4 * A;
-        lvb += RK_LEAVES * 4 * A;
-    }
-}
-
-// Tile walk with the accumulating-offset block layout (gnx_gbt_set_kernel 15): conflict-free feature loads
-// and one predicated add per level.
-template <int AT>
-__device__ __forceinline__ void gbt_rank_walk_to(int A, uint32_t row, const GbtTopW& top, const uint32_t* __restrict__ blk,
-                                                 const float* __restrict__ lv, int rounds, float* psum) {
-    constexpr int AMAX = AT ? AT : GBT_MAX_A;
-#pragma unroll
-    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
-    int tbase = 0;
-    const unsigned char* bb = reinterpret_cast<const unsigned char*>(blk);
-    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
-#pragma unroll 1
-    for (int rd = 0; rd < rounds; rd++) {
-#pragma unroll
-        for (int c = 0; c < AMAX; c++) {
-            if (c < A) {
-                const uint2 t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
-                const bool b0 = gnx_lds_u32(row + t0.y) > t0.x;
-                const uint2 n1 = b0 ? t2 : t1;
-                uint32_t o = b0 ? 32u : 0u;
-                gnx_add_if_gt(o, gnx_lds_u32(row + n1.y), n1.x, 16u);
-                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + o);
-                gnx_add_if_gt(o, gnx_lds_u32(row + ((n2 & 0xffffu) << 7)), n2, 8u);
-                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + 4 + o);
-                gnx_add_if_gt(o, gnx_lds_u32(row + ((n3 & 0xffffu) << 7)), n3, 4u);
-                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
-            }
-        }
-        tbase += 3 * A;
-        bb += RK_BLOCK * 4 * A;
-        lvb += RK_LEAVES * 4 * A;
-    }
-}
-
-// The same walk with one-word tree tops (k << 16 | feat) in the parameter bank: half the constant-cache footprint.
-template <int AT>
-__device__ __forceinline__ void gbt_rank_walk_to(int A, uint32_t row, const GbtTopC& top, const uint32_t* __restrict__ blk,
-                                                 const float* __restrict__ lv, int rounds, float* psum) {
-    constexpr int AMAX = AT ? AT : GBT_MAX_A;
-#pragma unroll
-    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
-    int tbase = 0;
-    const unsigned char* bb = reinterpret_cast<const unsigned char*>(blk);
-    const unsigned char* lvb = reinterpret_cast<const unsigned char*>(lv);
-#pragma unroll 1
-    for (int rd = 0; rd < rounds; rd++) {
-#pragma unroll
-        for (int c = 0; c < AMAX; c++) {
-            if (c < A) {
-                const uint32_t t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
-                const bool b0 = gnx_lds_u32(row + ((t0 & 0xffffu) << 7)) > t0;
-                const uint32_t n1 = b0 ? t2 : t1;
-                uint32_t o = b0 ? 32u : 0u;
-                gnx_add_if_gt(o, gnx_lds_u32(row + ((n1 & 0xffffu) << 7)), n1, 16u);
-                const uint32_t n2 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + o);
-                gnx_add_if_gt(o, gnx_lds_u32(row + ((n2 & 0xffffu) << 7)), n2, 8u);
-                const uint32_t n3 = *reinterpret_cast<const uint32_t*>(bb + c * (RK_BLOCK * 4) + 4 + o);
-                gnx_add_if_gt(o, gnx_lds_u32(row + ((n3 & 0xffffu) << 7)), n3, 4u);
-                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lvb + c * (RK_LEAVES * 4) + o));
-            }
-        }
-        tbase += 3 * A;
-        bb += RK_BLOCK * 4 * A;
-        lvb += RK_LEAVES * 4 * A;
-    }
-}
-
-// Wide-node variant (default of gbt_smooth): every node is two words { k << 16, byte offset of the
-// feature in a row }, so the feature address is one add (no mask) and the walk carries BYTE offsets
-// into the level-2 / level-3 / leaf arrays (select + shift-add per level instead of index arithmetic).
-// Top three nodes of every tree in the kernel parameter bank, nodes 3..14 (uint2) and leaves in
-// shared memory: 160 B per tree.
-
-template <int AT>
-__device__ __forceinline__ void gbt_rank_walk_w(int A, const unsigned char* __restrict__ row, const GbtTopW& top,
-                                                const unsigned char* __restrict__ lw, const unsigned char* __restrict__ lv,
-                                                int rounds, float* psum) {
-    constexpr int AMAX = AT ? AT : GBT_MAX_A;
-#pragma unroll
-    for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
-    int tbase = 0;
-#pragma unroll 1
-    for (int rd = 0; rd < rounds; rd++) {
-#pragma unroll
-        for (int c = 0; c < AMAX; c++) {
-            if (c < A) {
-                const uint2 t0 = top.w[tbase + 3 * c], t1 = top.w[tbase + 3 * c + 1], t2 = top.w[tbase + 3 * c + 2];
-                const bool b0 = *reinterpret_cast<const uint32_t*>(row + t0.y) > t0.x;
-                const uint2 n1 = b0 ? t2 : t1;
-                const bool b1 = *reinterpret_cast<const uint32_t*>(row + n1.y) > n1.x;
-                uint32_t o = (b0 ? 16u : 0u) + (b1 ? 8u : 0u);
-                const uint2 n2 = *reinterpret_cast<const uint2*>(lw + c * (RK_LOWER * 8) + o);
-                const bool b2 = *reinterpret_cast<const uint32_t*>(row + n2.y) > n2.x;
-                o = 2u * o + (b2 ? 8u : 0u);
-                const uint2 n3 = *reinterpret_cast<const uint2*>(lw + c * (RK_LOWER * 8) + 32 + o);
-                const bool b3 = *reinterpret_cast<const uint32_t*>(row + n3.y) > n3.x;
-                o += b3 ? 4u : 0u;
-                psum[c] = GNX_FADD(psum[c], *reinterpret_cast<const float*>(lv + c * (RK_LEAVES * 4) + o));
-            }
-        }
-        tbase += 3 * A;
-        lw += RK_LOWER * 8 * A;
-        lv += RK_LEAVES * 4 * A;
-    }
-}
-
 // One tree of the rank-form forest for one row: returns the leaf value.
 __device__ __forceinline__ float gbt_rank_tree(const unsigned char* __restrict__ row, const uint4 t4,
                                                const uint32_t* __restrict__ lw, const float* __restrict__ lv) {
@@ -421,21 +237,26 @@ struct gnx_gbt {
     gnx::GbtDev d;
     int device;
     void* d_blob;
-    size_t forest_bytes;     // nodes + leaves, contiguous (for the shared-memory resident copy)
-    size_t rank_forest_bytes;  // lower | leaves | top, contiguous (shared-memory image of the fast path)
+    size_t forest_bytes;        // nodes + leaves, contiguous (for the shared-memory resident copy of the generic kernel)
+    size_t rank_forest_bytes;   // lower | leaves | top, contiguous: image of the one-word row walk (also what gnofix stages)
     const unsigned char* rank_forest;
-    int use_rank;            // 1 = rank-form kernel when eligible (default), 0 = generic float traversal
-    gnx::GbtTopC* h_topc;    // host copy of the top nodes for the parameter-bank variant (NULL if T too large)
-    gnx::GbtTopW* h_topw;    // wide-node variant: top nodes (parameter bank) ...
-    const unsigned char* wide_forest;  // ... and lower uint2 [T][12] | leaves [T][16] (shared-memory image)
-    size_t wide_forest_bytes;
-    gnx::GbtTopC* h_toptn;   // tile variants with one-word tops (k << 16 | feat): gnx_gbt_set_kernel 16
-    gnx::GbtTopW* h_topt;    // tile variant: top nodes { k << 16, feat * 128 } (parameter bank) ...
-    const unsigned char* tile_forest;  // ... and lower u32 [T][12] | leaves [T][16], node = (k << 16) | feat
-    size_t tile_forest_bytes;
-    const unsigned char* tblock_forest; // tile + accumulating-offset variant: block u32 [T][16] (feature-index form) | leaves
-    size_t tblock_forest_bytes;
-    const unsigned char* block_forest;  // accumulating-offset variant: block u32 [T][16] | leaves [T][16]
+    int use_rank;               // 1 = rank-form kernels when eligible (default), 0 = generic float traversal
+    gnx::GbtTopC* h_topc;       // row kernel: tree tops (k << 16 | byte offset) for the parameter bank (NULL if T too large)
+    const unsigned char* block_forest;  // row kernel, accumulating-offset walk: block u32 [T][16] | leaves [T][16]
     size_t block_forest_bytes;
-    int variant;             // rank-form flavour: 2 wide nodes (default when eligible), 1 narrow + parameter-bank tops, 0 narrow
+    // tile kernel (gbt_tile.cu): node word = (k << 17) | (feature << 7); per tree one 128-byte record
+    // { block u32 [16], leaves f32 [16] }; tree tops in the parameter bank
+    gnx::GbtTileTop* h_tiletop;   // 4 words per tree
+    gnx::GbtTopC* h_tiletop3;     // 3 words per tree (GNX_GBT_TOPW=3)
+    int tile_top_words;
+    const unsigned char* tile_forest;
+    size_t tile_forest_bytes;
+    int variant;                // 0 row kernel / one-word walk, 4 row kernel / block walk, 6 tile kernel; -1 = choose per call
 };
+
+namespace gnx {
+// gbt_tile.cu: K4a (rank transform into hap-block-interleaved u16 tiles) + K4b (tile walk).  Returns 0 when it ran,
+// -1 when the shape does not fit the tile kernel (caller falls back to the row kernel), > 0 on error.
+int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, float* proba_dev, int32_t* label_dev,
+                    cudaStream_t st);
+}  // namespace gnx

@@ -1,0 +1,315 @@
+// gbt_tile.cu -- K4, tile form: the production kernel of XGB_Smoother.predict_proba / predict
+// (reference src/Smooth/utils.py:4-29 slide_window + src/Smooth/models.py:14-20 xgboost predict_proba +
+// src/Smooth/smooth.py:61 argmax) for batches of haplotypes.
+//
+// The walk of a depth-4 tree is four data-dependent feature loads, two node loads and one leaf load:
+// seven shared-memory wavefronts per warp and tree is the floor of any layout in which a lane owns a row,
+// and the kernel is built to sit on that floor:
+//   * lane = haplotype, warp = window.  The rank tile is lane-interleaved -- word (slot * A + a) * 32 + lane --
+//     so a feature load hits bank `lane` whatever node each lane has reached: no bank conflicts under
+//     divergence (the row kernel, lanes = windows, pays ~1.2 conflict wavefronts per tree).
+//   * node word = (k << 17) | (feature << 7): `rank << 17 > word` is the split test `!(x < thr)` and
+//     `word & 0x1ff80` is the byte offset of the feature row in the tile, so a level costs
+//     LDS node, LOP3 (mask | lane * 4), LDS feature, ISETP, predicated IADD.
+//   * per tree one 128-byte record { 16-word block, 16 leaves } addressed by ONE accumulating byte offset
+//     o = 32 b0 + 16 b1 + 8 b2 + 4 b3 (level-2 node at block + o, level-3 node at block + 4 + o, leaf at
+//     leaves + o); lanes of a warp read distinct banks or the same word.
+//   * the top three nodes of every tree come from the kernel parameter bank (warp-uniform: constant cache).
+//   * a warp walks two windows at once (rows wl and wl + 32 of the tile): the uniform work per tree is
+//     shared and there are 2 * A independent dependency chains in flight.
+// K4a turns the float32 base probabilities into their exact ranks (u16) once, written in the order the
+// tiles are staged in: R2[haplotype block][padded slot][class][32 lanes], reflect padding materialised.
+#include <algorithm>
+
+#include "gbt_smooth.cuh"
+
+namespace gnx {
+
+__device__ __forceinline__ uint32_t gnx_lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float gnx_lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+
+constexpr int TILE_WARPS = RK_THREADS / 32;
+constexpr uint32_t TILE_FMASK = 0x1ff80u;   // feature << 7 field of a node word
+
+// ---------------------------------------------------------------- K4a: rank transform
+// B f32 [N, W, A] -> R2 u16 [ceil(N/32)][Wp = W + S - 1][A][32]; NaN -> 0xFFFF, lanes beyond N -> 0.
+// lane = haplotype of the block (the 64-byte rows of R2 are written whole); a warp owns a run of consecutive
+// elements, so the 32-byte sectors its lanes read (one per haplotype) are reused from L1 for the next 7 elements.
+constexpr int RANK_RUN = 64;
+__global__ void __launch_bounds__(256)
+gbt_rank_tile_kernel(const float* __restrict__ thr, int K, int table_in_smem, const float* __restrict__ B, int64_t N, int W,
+                     int A, int S, uint16_t* __restrict__ R2) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float* tab = thr;
+    if (table_in_smem) {
+        float* t = reinterpret_cast<float*>(smem);
+        for (int i = threadIdx.x; i < K; i += blockDim.x) t[i] = __ldg(thr + i);
+        __syncthreads();
+        tab = t;
+    }
+    int top = 1;
+    while (top * 2 <= K) top *= 2;
+    const int pad = (S + 1) / 2, Wp = W + S - 1, E = Wp * A;
+    const int runs = (E + RANK_RUN - 1) / RANK_RUN;
+    const int64_t nhb = (N + 31) / 32, items = nhb * runs;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = warp0; it < items; it += nwarps) {
+        const int64_t hb = it / runs;
+        const int e0 = (int)(it - hb * runs) * RANK_RUN, e1 = min(e0 + RANK_RUN, E);
+        const int64_t n = hb * 32 + lane;
+        const float* bn = B + n * (int64_t)W * A;
+        uint16_t* out = R2 + (hb * E + e0) * 32 + lane;
+        int j = e0 / A, a = e0 - j * A;
+        for (int e = e0; e < e1; e++) {
+            uint16_t r = 0;
+            if (n < N) {
+                const float x = __ldg(bn + (int64_t)spad_to_orig(j, W, pad) * A + a);
+                int lo = 0;  // #{i : tab[i] <= x}
+                if (K > 0)
+                    for (int step = top; step; step >>= 1)
+                        if (lo + step <= K && tab[lo + step - 1] <= x) lo += step;
+                r = (x != x) ? (uint16_t)0xFFFFu : (uint16_t)lo;
+            }
+            *out = r;
+            out += 32;
+            if (++a == A) { a = 0; j++; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K4b: tile walk
+// (n & TILE_FMASK) | lane4 as ONE opaque LOP3: left to the compiler it is re-associated into mask + (row base + lane4),
+// a second (per-thread) add, instead of staying a per-thread offset next to the uniform row base of the load.
+__device__ __forceinline__ uint32_t gnx_feat_off(uint32_t n, uint32_t lane4) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(n), "n"(TILE_FMASK), "r"(lane4));
+    return d;
+}
+
+// One tree for one row.  rowu = shared address of the row's first tile word (warp-uniform), rowl = rowu + lane * 4,
+// lane4 = lane * 4, rec = shared address of the tree's 128-byte record (warp-uniform).
+__device__ __forceinline__ float gbt_tile_tree(uint32_t rowu, uint32_t rowl, uint32_t lane4, uint32_t t0, uint32_t t1, uint32_t t2,
+                                               uint32_t a0, uint32_t rec) {
+    const bool b0 = gnx_lds_u32(rowl + a0) > t0;
+    const uint32_t n1 = b0 ? t2 : t1;
+    uint32_t o = b0 ? 32u : 0u;
+    gnx_add_if_gt(o, gnx_lds_u32(rowu + gnx_feat_off(n1, lane4)), n1, 16u);
+    const uint32_t n2 = gnx_lds_u32(rec + o);
+    gnx_add_if_gt(o, gnx_lds_u32(rowu + gnx_feat_off(n2, lane4)), n2, 8u);
+    const uint32_t n3 = gnx_lds_u32(rec + 4u + o);
+    gnx_add_if_gt(o, gnx_lds_u32(rowu + gnx_feat_off(n3, lane4)), n3, 4u);
+    return gnx_lds_f32(rec + 64u + o);
+}
+
+template <typename TOPT> struct TileTopLoad;
+template <> struct TileTopLoad<GbtTileTop> {   // one 16-byte uniform load: nodes 0, 1, 2 and node 0's feature offset
+    static __device__ __forceinline__ uint4 get(const GbtTileTop& t, int i) { return t.q[i]; }
+};
+template <> struct TileTopLoad<GbtTopC> {      // three words per tree (smaller constant-cache footprint)
+    static __device__ __forceinline__ uint4 get(const GbtTopC& t, int i) {
+        const uint32_t t0 = t.w[3 * i];
+        return make_uint4(t0, t.w[3 * i + 1], t.w[3 * i + 2], t0 & TILE_FMASK);
+    }
+};
+
+template <int AT, typename TOPT>
+__global__ void __launch_bounds__(RK_THREADS, 1)
+gbt_smooth_tile_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes,
+                       uint32_t tile_bytes, const uint16_t* __restrict__ R2, const float* __restrict__ B, int64_t N, int W, int nseg, int Lseg,
+                       float* __restrict__ proba, int32_t* __restrict__ label) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int A = AT ? AT : m.A;
+    constexpr int AMAX = AT ? AT : GBT_MAX_A;
+    // shared memory: [ rank tile | forest records ].  A warp always walks rows `warp` and `warp + 32` of the tile,
+    // also when the segment is shorter: such rows read past the staged slots into the forest image (valid shared
+    // memory -- the launcher checks the bound -- garbage values) and are not written.
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(forest_img);
+        uint4* dst = reinterpret_cast<uint4*>(smem + tile_bytes);
+        for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t forest_s = tile_s + tile_bytes;
+    const int pad = (m.S + 1) / 2;
+    const int Wp = W + m.S - 1;
+    const int Lslots = Lseg + m.S - 1;
+    const int rounds = m.T / A;
+    // a warp reduction lands in a uniform register: the compiler then knows that the warp index (and the row bases
+    // derived from it) are warp-uniform and addresses feature loads as [lane part + uniform row base]
+    const int warp = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const int64_t nhb = (N + 31) / 32;
+    for (int64_t t = blockIdx.x; t < nhb * nseg; t += gridDim.x) {
+        const int64_t hb = t / nseg;
+        const int sg = (int)(t - hb * nseg);
+        const int64_t n = hb * 32 + lane;
+        const int w0 = sg * Lseg;
+        __syncthreads();
+        // stage: the tile's slots are one contiguous run of R2; a uint4 holds 8 lanes of one element
+        int saw_nan = 0;
+        {
+            const int slots = min(Lslots, Wp - w0);
+            const uint4* src = reinterpret_cast<const uint4*>(R2 + ((hb * Wp + w0) * (int64_t)A) * 32);
+            const int nq = slots * A * 4;
+            for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+                const uint4 v = __ldg(src + q);
+                uint4 lo, hi;
+                lo.x = v.x << 17; lo.y = (v.x >> 16) << 17; lo.z = v.y << 17; lo.w = (v.y >> 16) << 17;
+                hi.x = v.z << 17; hi.y = (v.z >> 16) << 17; hi.z = v.w << 17; hi.w = (v.w >> 16) << 17;
+                // NaN marker 0xFFFF in either half of any word
+                saw_nan |= ((v.x & 0xffffu) == 0xffffu) | ((v.x >> 16) == 0xffffu) | ((v.y & 0xffffu) == 0xffffu) | ((v.y >> 16) == 0xffffu) |
+                           ((v.z & 0xffffu) == 0xffffu) | ((v.z >> 16) == 0xffffu) | ((v.w & 0xffffu) == 0xffffu) | ((v.w >> 16) == 0xffffu);
+                uint4* dst = reinterpret_cast<uint4*>(tile + (size_t)q * 8);
+                dst[0] = lo;
+                dst[1] = hi;
+            }
+        }
+        const int slow = __syncthreads_or(saw_nan);
+        // The walk runs in warp-uniform control flow whatever the data (uniform registers for the record and row
+        // bases): rows beyond the segment / chromosome are walked and not written; a tile holding NaN is walked too
+        // (harmlessly: every address is valid) and then redone by the generic traversal.
+        const int last = min(Lseg, W - w0) - 1;
+        const int wla = warp, wlb = warp + TILE_WARPS;
+        {
+            const uint32_t rau = tile_s + (uint32_t)(wla * A * 128), rbu = tile_s + (uint32_t)(wlb * A * 128);
+            const uint32_t ral = rau + lane4, rbl = rbu + lane4;
+            float pa[AMAX], pb[AMAX];
+#pragma unroll
+            for (int c = 0; c < AMAX; c++) pa[c] = pb[c] = 0.f;
+            int tb = 0;
+            uint32_t rec = forest_s;
+#pragma unroll 1
+            for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+                for (int c = 0; c < AMAX; c++) {
+                    if (c < A) {
+                        const uint4 tp = TileTopLoad<TOPT>::get(topc, tb + c);
+                        pa[c] = GNX_FADD(pa[c], gbt_tile_tree(rau, ral, lane4, tp.x, tp.y, tp.z, tp.w, rec + c * 128));
+                        pb[c] = GNX_FADD(pb[c], gbt_tile_tree(rbu, rbl, lane4, tp.x, tp.y, tp.z, tp.w, rec + c * 128));
+                    }
+                }
+                tb += A;
+                rec += 128 * A;
+            }
+            if (n < N && !slow) {
+                if (warp <= last) {
+                    const int64_t ra = n * W + w0 + wla;
+                    gbt_finish<AT>(m, pa, proba ? proba + ra * A : nullptr, label ? label + ra : nullptr);
+                }
+                if (warp + TILE_WARPS <= last) {
+                    const int64_t rb = n * W + w0 + wlb;
+                    gbt_finish<AT>(m, pb, proba ? proba + rb * A : nullptr, label ? label + rb : nullptr);
+                }
+            }
+        }
+        if (slow) {
+            // NaN inputs follow each node's default child: generic float traversal, one haplotype of the
+            // tile at a time, its padded float row staged where the rank tile was
+            float* bp = reinterpret_cast<float*>(tile);
+            for (int h = 0; h < 32; h++) {
+                const int64_t nh = hb * 32 + h;
+                if (nh >= N) break;
+                __syncthreads();
+                for (int e = threadIdx.x; e < Lslots * A; e += blockDim.x) {
+                    const int jl = e / A, a = e - jl * A;
+                    const int j = w0 + jl;
+                    bp[e] = (j < Wp) ? __ldg(B + (nh * W + spad_to_orig(j, W, pad)) * A + a) : 0.f;
+                }
+                __syncthreads();
+                for (int wl = threadIdx.x; wl < Lseg && w0 + wl < W; wl += blockDim.x) {
+                    float psum[AMAX];
+                    gbt_eval_row<AT>(m, m.nodes, m.leaves, bp + (size_t)wl * A, psum);
+                    const int64_t row = nh * W + w0 + wl;
+                    gbt_finish<AT>(m, psum, proba ? proba + row * A : nullptr, label ? label + row : nullptr);
+                }
+            }
+        }
+    }
+}
+
+int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, float* proba_dev, int32_t* label_dev, cudaStream_t st) {
+    const int A = m->d.A, S = m->d.S;
+    const size_t smem_max = 227 * 1024;
+    const size_t slot_bytes = (size_t)A * 128;
+    if (m->tile_forest_bytes + 64 >= smem_max) return -1;
+    const size_t room = smem_max - m->tile_forest_bytes;
+    const int64_t fit = (int64_t)(room / slot_bytes) - (S - 1);
+    const int Lmax = (int)std::min<int64_t>(fit, 2 * TILE_WARPS);
+    if (Lmax < TILE_WARPS && Lmax < W) return -1;   // a tile must give every warp a window
+    const int nseg = (int)ceil_div(W, std::min(Lmax, W));
+    const int Lseg = (int)ceil_div(W, nseg);
+    const int Wp = W + S - 1;
+    const int64_t nhb = ceil_div(N, 32);
+    const size_t tile_bytes = (size_t)(Lseg + S - 1) * slot_bytes;
+    const size_t smem = tile_bytes + m->tile_forest_bytes;
+    if ((size_t)(2 * TILE_WARPS + S - 1) * slot_bytes > smem) return -1;   // rows past the segment must stay inside shared memory
+    // the rank scratch comes from the device's stream-ordered pool; keep freed blocks in the pool across calls
+    {
+        static bool pool_kept[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !pool_kept[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_kept[dev] = true;
+        }
+    }
+    uint16_t* R2 = nullptr;
+    GNX_CUDA(cudaMallocAsync((void**)&R2, (size_t)nhb * Wp * A * 32 * sizeof(uint16_t), st));
+    {
+        const int in_smem = (size_t)m->d.K * 4 <= 132 * 1024;
+        const size_t rsm = in_smem ? (size_t)m->d.K * 4 : 0;
+        GNX_CUDA(cudaFuncSetAttribute(gbt_rank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(132 * 1024)));
+        const int64_t items = nhb * ceil_div((int64_t)Wp * A, RANK_RUN);
+        const int per_sm = rsm > 56 * 1024 ? 1 : (rsm > 24 * 1024 ? 3 : 6);
+        const int grid = (int)std::min<int64_t>(ceil_div(items, 8), (int64_t)sm_count() * per_sm);
+        gbt_rank_tile_kernel<<<grid, 256, rsm, st>>>(m->d.thr_table, m->d.K, in_smem, B_dev, N, W, A, S, R2);
+        GNX_CUDA(cudaGetLastError());
+    }
+    const int64_t tiles = nhb * nseg;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count());
+#define LAUNCHT(AT, TOPT, TOPV)                                                                                                \
+    do {                                                                                                                       \
+        GNX_CUDA(cudaFuncSetAttribute(gbt_smooth_tile_kernel<AT, TOPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gbt_smooth_tile_kernel<AT, TOPT><<<grid, RK_THREADS, smem, st>>>(TOPV, m->d, m->tile_forest, m->tile_forest_bytes, (uint32_t)tile_bytes, \
+                                                                         R2, B_dev, N, W, nseg, Lseg, proba_dev, label_dev);  \
+    } while (0)
+#define CALLT(AT)                                                  \
+    do {                                                           \
+        if (m->tile_top_words == 4) {                              \
+            LAUNCHT(AT, GbtTileTop, *m->h_tiletop);                \
+        } else {                                                   \
+            LAUNCHT(AT, GbtTopC, *m->h_tiletop3);                  \
+        }                                                          \
+    } while (0)
+    switch (A) {
+        case 2: CALLT(2); break;
+        case 3: CALLT(3); break;
+        case 4: CALLT(4); break;
+        case 5: CALLT(5); break;
+        case 6: CALLT(6); break;
+        case 7: CALLT(7); break;
+        case 8: CALLT(8); break;
+        default: CALLT(0); break;
+    }
+#undef CALLT
+#undef LAUNCHT
+    GNX_CUDA(cudaGetLastError());
+    GNX_CUDA(cudaFreeAsync(R2, st));
+    return 0;
+}
+
+}  // namespace gnx

@@ -378,6 +378,14 @@ extern "C" int gnx_upload_haplotypes(const int8_t* X_host, int64_t N, int64_t ld
  * (they are re-created on demand); the calibration is kept. */
 extern "C" int gnx_release_workspace(void) {
     std::lock_guard<std::mutex> lock(g_ws_mu);
+    {   // the smoother's rank scratch lives in the stream-ordered pool (gbt_tile.cu keeps freed blocks there)
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+    }
     if (g_ws.device >= 0) {
         int cur = 0;
         if (cudaGetDevice(&cur) == cudaSuccess && cur != g_ws.device) {

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GNX_VERSION 110 /* 0.1.1: packed host transfer, K7, host-side I/O entry points */
+#define GNX_VERSION 120 /* 0.2.0: tile smoother kernel, whole-pipeline host entry points */
 
 typedef struct gnx_lr gnx_lr_t;   /* per-window logistic-regression base (K1) */
 typedef struct gnx_gbt gnx_gbt_t; /* gradient-boosted-tree smoother (K4)      */
@@ -97,15 +97,15 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
                          const uint8_t* default_left, const float* leaf,
                          const int32_t* tree_offsets, const float* base_margin);
 void gnx_gbt_model_destroy(gnx_gbt_t* m);
-/* kernel selector: 0 = rank-form kernel (default; depth <= 4 forests, falls back by itself
- *                      otherwise), 1 = generic float traversal (cross-check; same results);
- *                  10 .. 16 = rank-form kernel with a given layout: 10 one-word nodes / 11 one-word
- *                      nodes + tree tops in the parameter bank / 12 two-word nodes / 13 lane-
- *                      interleaved haplotype tiles behind a separate rank pass / 14 block layout
- *                      with one accumulating byte offset per walk (the default) / 15 tiles + block
- *                      layout, two-word tree tops / 16 the same with one-word tree tops (fastest
- *                      measured, 3 % ahead of 14).  Same results; measurements in profiles/README.md.
- * Environment GNX_GBT_VARIANT=0..6 picks the layout at model-create time (profiling). */
+/* kernel selector (same results from every one of them):
+ *   0  = default: rank-form kernels for depth <= 4 forests -- the tile kernel (lanes = 32 haplotypes, warps =
+ *        windows, conflict-free lane-interleaved rank tiles behind a u16 rank pass) for batches of >= 24
+ *        haplotypes, the row kernel (lanes = windows of one haplotype) below that; the generic kernel otherwise;
+ *   1  = generic float traversal (cross-check; any depth <= 8);
+ *   10 = row kernel, one-word nodes and index arithmetic (the walk gnofix uses);
+ *   14 = row kernel, block layout with one accumulating byte offset per walk;
+ *   16 = tile kernel whatever the batch size (falls back to the row kernel when the shape does not fit).
+ * Environment GNX_GBT_VARIANT=0|4|6 picks 10|14|16 at model-create time (profiling). */
 int gnx_gbt_set_kernel(gnx_gbt_t* m, int which);
 /* proba_dev [N,W,A] float32 and label_dev [N,W] int32; either may be NULL */
 int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, float* proba_dev,

@@ -1,12 +1,12 @@
 """K4 timing probe: python scripts/k4_probe.py [N] -- times the rank-form flavours of gnx_gbt_smooth
-(gnx_gbt_set_kernel 11 narrow / 12 wide / 13 tile) on the bench forest and checks they agree bit for bit."""
+(gnx_gbt_set_kernel 10 / 14 row kernel walks, 16 tile kernel) on the bench forest and checks they agree bit for bit."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from gnomix_b200 import synth, _lib
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-kinds = [int(k) for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["11", "12", "13"])]
+kinds = [int(k) for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["14", "16"])]
 geom = synth.GEOMETRY["chr1"]
 C, M, A, S, morgans = geom
 W = C // M

@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol(libgnx):
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (gnx_[a-z0-9_]+)", out))
     assert declared <= exported, declared - exported
-    assert libgnx.gnx_version() == 110
+    assert libgnx.gnx_version() == 120
     assert libgnx.gnx_release_workspace() == 0      # nothing allocated: a no-op that must not need a device
 
 
