@@ -6,5 +6,6 @@ from .gbt import GBTForest  # noqa: F401
 from .base import Base, LogisticRegressionBase, CovRSKBase  # noqa: F401
 from .smooth import Smoother, XGB_Smoother, CRF_Smoother  # noqa: F401
 from .model import Gnomix  # noqa: F401
+from .pickle_compat import load_model  # noqa: F401
 
 __version__ = "0.1.0"

@@ -32,6 +32,8 @@ _SIGS = {
     "gnx_gbt_model_create": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gnx_gbt_model_destroy": (None, [c_vp]),
     "gnx_gbt_set_kernel": (C.c_int, [c_vp, C.c_int]),
+    "gnx_gbt_set_profile": (C.c_int, [c_vp, C.c_int]),
+    "gnx_gbt_last_phase_ms": (C.c_int, [c_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gnx_gbt_smooth": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp]),
     "gnx_gbt_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "gnx_crf_model_create": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int, c_vp, c_vp]),

@@ -304,6 +304,9 @@ class CovRSKBase(Base):
         key = torch.cuda.current_device()
         h = self._handles.get(key)
         if h is None:
+            if getattr(self, "_fitted", None) is None:   # unpickled from the reference: derive the arrays from its SVCs
+                from .pickle_compat import adopt_covrsk
+                adopt_covrsk(self)
             f = self._fitted
             h = self._make_handle(self.sv_rows, f["n_support"], f["dual_coef"], f["intercept"], f["probA"], f["probB"])
             self._handles[key] = h

@@ -20,14 +20,10 @@ from . import postprocess as pp
 
 
 def load_model(path_to_model, verbose=True):
-    """gnomix.py:26-35 (plain or gzip pickle of the whole Gnomix object)."""
-    if verbose:
-        print("Loading model...")
-    if path_to_model[-3:] == ".gz":
-        with gzip.open(path_to_model, "rb") as f:
-            return pickle.load(f)
-    with open(path_to_model, "rb") as f:
-        return pickle.load(f)
+    """gnomix.py:26-35 (plain or gzip pickle of the whole Gnomix object) -- reference-written pickles included
+    (scikit-learn / xgboost / sklearn-crfsuite objects are converted, not imported: gnomix_b200/pickle_compat.py)."""
+    from .pickle_compat import load_model as _load
+    return _load(path_to_model, verbose=verbose)
 
 
 def read_headers(vcf_file):

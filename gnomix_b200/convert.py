@@ -17,37 +17,12 @@ from .gbt import GBTForest
 
 
 def forest_from_xgboost_json(obj, num_class=None, n_features=None) -> GBTForest:
-    """xgboost JSON model (dict, JSON string or path) -> GBTForest.  Schema: learner.gradient_booster.
-    model.trees[t] holds parallel arrays left_children / right_children (-1 = leaf), split_indices,
-    split_conditions (split threshold, or the leaf value at a leaf), default_left; tree_info[t] is the
-    class of tree t; learner_model_param has base_score / num_class / num_feature."""
+    """xgboost JSON model (dict, JSON string or path) -> GBTForest (schema: xgb_io.forest_from_model_dict)."""
+    from .xgb_io import forest_from_model_dict
     if isinstance(obj, (str, bytes)):
         txt = obj if isinstance(obj, str) else obj.decode()
         obj = json.loads(txt) if txt.lstrip().startswith("{") else json.load(open(txt))
-    learner = obj["learner"]
-    lmp = learner["learner_model_param"]
-    A = int(num_class or max(int(lmp.get("num_class", "0")), 1))
-    F = int(n_features or lmp["num_feature"])
-    base_score = float(lmp.get("base_score", "0.5"))
-    gb = learner["gradient_booster"]
-    model = gb["model"] if "model" in gb else gb["gbtree"]["model"]
-    trees, info = model["trees"], [int(v) for v in model["tree_info"]]
-    if A < 2:
-        raise ValueError("binary:logistic boosters are not a multi:softprob forest (the reference trains with num_class=A)")
-    assert len(trees) % A == 0 and all(info[t] == t % A for t in range(len(trees))), \
-        "tree t must belong to class t % A (xgboost multi:softprob layout)"
-    feat, thr, left, right, dl, leaf, offs = [], [], [], [], [], [], [0]
-    for tr in trees:
-        lc, rc = tr["left_children"], tr["right_children"]
-        for i in range(len(lc)):
-            if lc[i] == -1:
-                feat.append(-1); thr.append(0.0); left.append(0); right.append(0); dl.append(0)
-                leaf.append(np.float32(tr["split_conditions"][i]))
-            else:
-                feat.append(int(tr["split_indices"][i])); thr.append(np.float32(tr["split_conditions"][i]))
-                left.append(int(lc[i])); right.append(int(rc[i])); dl.append(1 if tr["default_left"][i] else 0); leaf.append(0.0)
-        offs.append(len(feat))
-    return GBTForest(A, F, feat, thr, left, right, dl, leaf, offs, np.full(A, base_score, dtype=np.float32))
+    return forest_from_model_dict(obj, num_class, n_features)
 
 
 def forest_to_xgboost_json(forest: GBTForest) -> dict:

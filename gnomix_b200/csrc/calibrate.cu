@@ -24,6 +24,8 @@ struct gnx_cal {
 
 namespace gnx {
 
+int cal_classes(const gnx_cal* m) { return m->A; }
+
 constexpr int CAL_MAX_A = 16;
 
 __device__ __forceinline__ double cal_interp64(const double* __restrict__ xp, const double* __restrict__ fp, int n, double x) {

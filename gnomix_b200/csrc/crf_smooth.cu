@@ -283,6 +283,10 @@ struct gnx_crf {
     void* d_blob;
 };
 
+namespace gnx {
+void crf_dims(const gnx_crf* m, int* A, int* L) { *A = m->d.A; *L = m->d.L; }
+}  // namespace gnx
+
 using namespace gnx;
 
 extern "C" {

@@ -296,6 +296,9 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->h_topc = nullptr;
     m->h_tiletop = nullptr;
     m->h_tiletop3 = nullptr;
+    m->rank_lut = nullptr;
+    m->profile = 0;
+    m->ev[0] = m->ev[1] = m->ev[2] = nullptr;
     m->tile_top_words = 4;
     m->tile_forest = nullptr;
     m->tile_forest_bytes = 0;
@@ -347,6 +350,10 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
                 m->h_tiletop->q[t] = make_uint4(t0, conv(top[(size_t)t * 4 + 1]), conv(top[(size_t)t * 4 + 2]), t0 & 0x1ff80u);
                 for (int k = 0; k < 3; k++) m->h_tiletop3->w[3 * t + k] = conv(top[(size_t)t * 4 + k]);
             }
+            if (gbt_rank_lut_build(m->d.thr_table, tab.data(), K, &m->rank_tmin, &m->rank_tmax, &m->rank_scale, &m->rank_lut)) {
+                gnx_gbt_model_destroy(m);
+                return 1;
+            }
             const char* tw = getenv("GNX_GBT_TOPW");
             m->tile_top_words = (tw && atoi(tw) == 3) ? 3 : 4;
             void* d_t = nullptr;
@@ -370,6 +377,9 @@ void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->tile_forest) cudaFree(const_cast<unsigned char*>(m->tile_forest));
     if (m->block_forest) cudaFree(const_cast<unsigned char*>(m->block_forest));
+    if (m->rank_lut) cudaFree(m->rank_lut);
+    for (int i = 0; i < 3; i++)
+        if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m->h_tiletop;
     delete m->h_tiletop3;
     delete m->h_topc;
@@ -484,6 +494,26 @@ int gnx_gbt_set_kernel(gnx_gbt_t* m, int which) {
         GNX_REQUIRE(v == 0 || (v == 4 && m->block_forest) || (v == 6 && m->tile_forest), "gnx_gbt_set_kernel: kernel %d not available for this forest", which);
         m->variant = v;
     }
+    return 0;
+}
+
+int gnx_gbt_set_profile(gnx_gbt_t* m, int on) {
+    GNX_REQUIRE(m != nullptr, "gnx_gbt_set_profile: NULL model");
+    if (on)
+        for (int i = 0; i < 3; i++)
+            if (!m->ev[i]) GNX_CUDA(cudaEventCreate(&m->ev[i]));
+    m->profile = on ? 1 : 0;
+    return 0;
+}
+
+int gnx_gbt_last_phase_ms(const gnx_gbt_t* m, float* rank_ms, float* walk_ms) {
+    GNX_REQUIRE(m != nullptr && m->ev[2], "gnx_gbt_last_phase_ms: profiling was not switched on (gnx_gbt_set_profile)");
+    GNX_CUDA(cudaEventSynchronize(m->ev[2]));
+    float a = 0.f, b = 0.f;
+    GNX_CUDA(cudaEventElapsedTime(&a, m->ev[0], m->ev[1]));
+    GNX_CUDA(cudaEventElapsedTime(&b, m->ev[1], m->ev[2]));
+    if (rank_ms) *rank_ms = a;
+    if (walk_ms) *walk_ms = b;
     return 0;
 }
 

@@ -17,6 +17,7 @@ constexpr int GBT_TILE_MAX_K = 32767;   // threshold indices (and ranks) must fi
 constexpr int GBT_TILE_MAX_F = 1023;    // feature << 7 must stay below bit 17
 constexpr int GBT_TILE_MAX_T = 1792;    // tree tops travel in the kernel parameter bank (28 KB of the 32 KB)
 constexpr int GBT_TILE_MIN_N = 24;      // below this many haplotypes the row kernel is used (lanes = haplotypes here)
+constexpr int GBT_RANK_CELLS = 8192;    // equal cells over the threshold range (rank pass of the tile kernel)
 
 // Heap-ordered complete forest.  Tree t: (2^D - 1) split nodes then 2^D leaves.
 // Shallower subtrees are padded with always-left splits whose both children carry
@@ -249,6 +250,10 @@ struct gnx_gbt {
     gnx::GbtTileTop* h_tiletop;   // 4 words per tree
     gnx::GbtTopC* h_tiletop3;     // 3 words per tree (GNX_GBT_TOPW=3)
     int tile_top_words;
+    uint32_t* rank_lut;           // [GBT_RANK_CELLS] first threshold of the cell | thresholds in it << 16
+    float rank_tmin, rank_tmax, rank_scale;
+    int profile;                  // gnx_gbt_set_profile: record events around the rank pass and the walk
+    cudaEvent_t ev[3];
     const unsigned char* tile_forest;
     size_t tile_forest_bytes;
     int variant;                // 0 row kernel / one-word walk, 4 row kernel / block walk, 6 tile kernel; -1 = choose per call
@@ -257,6 +262,7 @@ struct gnx_gbt {
 namespace gnx {
 // gbt_tile.cu: K4a (rank transform into hap-block-interleaved u16 tiles) + K4b (tile walk).  Returns 0 when it ran,
 // -1 when the shape does not fit the tile kernel (caller falls back to the row kernel), > 0 on error.
+int gbt_rank_lut_build(const float* tab_dev, const float* tab_host, int K, float* tmin, float* tmax, float* scale, uint32_t** lut_dev);
 int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, float* proba_dev, int32_t* label_dev,
                     cudaStream_t st);
 }  // namespace gnx

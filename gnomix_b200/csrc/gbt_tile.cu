@@ -20,6 +20,7 @@
 // K4a turns the float32 base probabilities into their exact ranks (u16) once, written in the order the
 // tiles are staged in: R2[haplotype block][padded slot][class][32 lanes], reflect padding materialised.
 #include <algorithm>
+#include <vector>
 
 #include "gbt_smooth.cuh"
 
@@ -41,22 +42,62 @@ constexpr uint32_t TILE_FMASK = 0x1ff80u;   // feature << 7 field of a node word
 
 // ---------------------------------------------------------------- K4a: rank transform
 // B f32 [N, W, A] -> R2 u16 [ceil(N/32)][Wp = W + S - 1][A][32]; NaN -> 0xFFFF, lanes beyond N -> 0.
+// rank(x) = #{i : tab[i] <= x}, exactly.  A binary search over the shared-memory table probes, at every level whose
+// step is a multiple of 32 words, ONE bank for the whole warp (measured: 139 wavefronts per warp and element, 9 ms at
+// 50 000 haplotypes).  Instead the threshold range [tab[0], tab[K-1]) is cut into GBT_RANK_CELLS equal cells:
+// cell(x) is a monotone function of x, so every threshold in a lower cell is < x and every threshold in a higher
+// cell is > x, and only the (on average ~1) thresholds sharing x's cell are compared.  lut[c] = first threshold of
+// cell c | number of thresholds in it << 16, built at model-create time from cell() evaluated ON THE DEVICE for
+// every threshold (the same instruction sequence as here, so host and device never disagree on a cell boundary).
+__device__ __forceinline__ int gbt_rank_cell(float x, float tmin, float scale) {
+    const int c = __float2int_rz(__fmul_rn(__fsub_rn(x, tmin), scale));
+    return min(max(c, 0), GBT_RANK_CELLS - 1);
+}
+
+__global__ void gbt_rank_cells_kernel(const float* __restrict__ tab, int K, float tmin, float scale, int* __restrict__ cell) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) cell[i] = gbt_rank_cell(tab[i], tmin, scale);
+}
+
+__device__ __forceinline__ uint32_t gbt_rank_lut(const float* __restrict__ tab, const uint32_t* __restrict__ lut, int K, float tmin,
+                                                 float tmax, float scale, float x) {
+    if (x != x) return 0xFFFFu;
+    if (K == 0 || x < tmin) return 0u;
+    if (x >= tmax) return (uint32_t)K;
+    const uint32_t e = lut[gbt_rank_cell(x, tmin, scale)];
+    int lo = (int)(e & 0xffffu), n = (int)(e >> 16);
+    if (n <= 4) {
+        while (n > 0 && tab[lo] <= x) { lo++; n--; }
+        return (uint32_t)lo;
+    }
+    int hi = lo + n;   // #{i : tab[i] <= x} within [lo, hi)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return (uint32_t)lo;
+}
+
 // lane = haplotype of the block (the 64-byte rows of R2 are written whole); a warp owns a run of consecutive
 // elements, so the 32-byte sectors its lanes read (one per haplotype) are reused from L1 for the next 7 elements.
 constexpr int RANK_RUN = 64;
 __global__ void __launch_bounds__(256)
-gbt_rank_tile_kernel(const float* __restrict__ thr, int K, int table_in_smem, const float* __restrict__ B, int64_t N, int W,
-                     int A, int S, uint16_t* __restrict__ R2) {
+gbt_rank_tile_kernel(const float* __restrict__ thr, const uint32_t* __restrict__ lut_g, int K, float tmin, float tmax, float scale,
+                     int table_in_smem, const float* __restrict__ B, int64_t N, int W, int A, int S, uint16_t* __restrict__ R2) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t* lut = lut_g;
     const float* tab = thr;
-    if (table_in_smem) {
-        float* t = reinterpret_cast<float*>(smem);
-        for (int i = threadIdx.x; i < K; i += blockDim.x) t[i] = __ldg(thr + i);
+    {
+        uint32_t* l = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < GBT_RANK_CELLS; i += blockDim.x) l[i] = __ldg(lut_g + i);
+        lut = l;
+        if (table_in_smem) {
+            float* t = reinterpret_cast<float*>(smem + GBT_RANK_CELLS * 4);
+            for (int i = threadIdx.x; i < K; i += blockDim.x) t[i] = __ldg(thr + i);
+            tab = t;
+        }
         __syncthreads();
-        tab = t;
     }
-    int top = 1;
-    while (top * 2 <= K) top *= 2;
     const int pad = (S + 1) / 2, Wp = W + S - 1, E = Wp * A;
     const int runs = (E + RANK_RUN - 1) / RANK_RUN;
     const int64_t nhb = (N + 31) / 32, items = nhb * runs;
@@ -71,19 +112,44 @@ gbt_rank_tile_kernel(const float* __restrict__ thr, int K, int table_in_smem, co
         int j = e0 / A, a = e0 - j * A;
         for (int e = e0; e < e1; e++) {
             uint16_t r = 0;
-            if (n < N) {
-                const float x = __ldg(bn + (int64_t)spad_to_orig(j, W, pad) * A + a);
-                int lo = 0;  // #{i : tab[i] <= x}
-                if (K > 0)
-                    for (int step = top; step; step >>= 1)
-                        if (lo + step <= K && tab[lo + step - 1] <= x) lo += step;
-                r = (x != x) ? (uint16_t)0xFFFFu : (uint16_t)lo;
-            }
+            if (n < N) r = (uint16_t)gbt_rank_lut(tab, lut, K, tmin, tmax, scale, __ldg(bn + (int64_t)spad_to_orig(j, W, pad) * A + a));
             *out = r;
             out += 32;
             if (++a == A) { a = 0; j++; }
         }
     }
+}
+
+// model-create half of the rank pass: the cell table (see above).  Returns 0 / non-zero like the C ABI.
+int gbt_rank_lut_build(const float* tab_dev, const float* tab_host, int K, float* tmin, float* tmax, float* scale, uint32_t** lut_dev) {
+    std::vector<uint32_t> lut(GBT_RANK_CELLS, 0u);
+    *tmin = K ? tab_host[0] : 0.f;
+    *tmax = K ? tab_host[K - 1] : 0.f;
+    const float span = *tmax - *tmin;
+    *scale = (K > 1 && span > 0.f && span < INFINITY) ? (float)GBT_RANK_CELLS / span : 0.f;
+    if (!(*scale == *scale) || *scale == INFINITY) *scale = 0.f;   // every x then lands in cell 0: still exact, just slower
+    if (K > 0) {
+        int* cell_dev = nullptr;
+        GNX_CUDA(cudaMalloc((void**)&cell_dev, (size_t)K * sizeof(int)));
+        gbt_rank_cells_kernel<<<(K + 255) / 256, 256>>>(tab_dev, K, *tmin, *scale, cell_dev);
+        std::vector<int> cell(K);
+        const cudaError_t e = cudaMemcpy(cell.data(), cell_dev, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(cell_dev);
+        GNX_CUDA(e);
+        std::vector<uint32_t> cnt(GBT_RANK_CELLS, 0u);
+        for (int i = 0; i < K; i++) {
+            GNX_REQUIRE(cell[i] >= 0 && cell[i] < GBT_RANK_CELLS && (i == 0 || cell[i] >= cell[i - 1]), "gnx_gbt_model_create: rank cells are not monotone");
+            cnt[cell[i]]++;
+        }
+        uint32_t start = 0;
+        for (int c = 0; c < GBT_RANK_CELLS; c++) {
+            lut[c] = start | (cnt[c] << 16);
+            start += cnt[c];
+        }
+    }
+    GNX_CUDA(cudaMalloc((void**)lut_dev, GBT_RANK_CELLS * sizeof(uint32_t)));
+    GNX_CUDA(cudaMemcpy(*lut_dev, lut.data(), GBT_RANK_CELLS * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return 0;
 }
 
 // ---------------------------------------------------------------- K4b: tile walk
@@ -269,16 +335,19 @@ int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, floa
     }
     uint16_t* R2 = nullptr;
     GNX_CUDA(cudaMallocAsync((void**)&R2, (size_t)nhb * Wp * A * 32 * sizeof(uint16_t), st));
+    if (m->profile) GNX_CUDA(cudaEventRecord(m->ev[0], st));
     {
-        const int in_smem = (size_t)m->d.K * 4 <= 132 * 1024;
-        const size_t rsm = in_smem ? (size_t)m->d.K * 4 : 0;
-        GNX_CUDA(cudaFuncSetAttribute(gbt_rank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(132 * 1024)));
+        const int in_smem = (size_t)m->d.K * 4 <= 96 * 1024;
+        const size_t rsm = GBT_RANK_CELLS * 4 + (in_smem ? (size_t)m->d.K * 4 : 0);
+        GNX_CUDA(cudaFuncSetAttribute(gbt_rank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GBT_RANK_CELLS * 4 + 96 * 1024)));
         const int64_t items = nhb * ceil_div((int64_t)Wp * A, RANK_RUN);
-        const int per_sm = rsm > 56 * 1024 ? 1 : (rsm > 24 * 1024 ? 3 : 6);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / rsm));
         const int grid = (int)std::min<int64_t>(ceil_div(items, 8), (int64_t)sm_count() * per_sm);
-        gbt_rank_tile_kernel<<<grid, 256, rsm, st>>>(m->d.thr_table, m->d.K, in_smem, B_dev, N, W, A, S, R2);
+        gbt_rank_tile_kernel<<<grid, 256, rsm, st>>>(m->d.thr_table, m->rank_lut, m->d.K, m->rank_tmin, m->rank_tmax, m->rank_scale, in_smem,
+                                                     B_dev, N, W, A, S, R2);
         GNX_CUDA(cudaGetLastError());
     }
+    if (m->profile) GNX_CUDA(cudaEventRecord(m->ev[1], st));
     const int64_t tiles = nhb * nseg;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count());
 #define LAUNCHT(AT, TOPT, TOPV)                                                                                                \
@@ -308,6 +377,7 @@ int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, floa
 #undef CALLT
 #undef LAUNCHT
     GNX_CUDA(cudaGetLastError());
+    if (m->profile) GNX_CUDA(cudaEventRecord(m->ev[2], st));
     GNX_CUDA(cudaFreeAsync(R2, st));
     return 0;
 }

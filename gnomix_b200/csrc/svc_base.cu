@@ -328,6 +328,10 @@ struct gnx_svc {
     void* d_blob;
 };
 
+namespace gnx {
+void svc_dims(const gnx_svc* m, int64_t* C, int* W, int* A) { *C = m->d.C; *W = m->d.W; *A = m->d.A; }
+}  // namespace gnx
+
 using namespace gnx;
 
 extern "C" {

@@ -58,10 +58,18 @@ class GBTForest:
         cond32 = nextafter32(floor32(t64), +inf) -- identical on every float32 x."""
         preds = hgb._predictors
         A = len(preds[0])
+        binary = (A == 1)   # HGB fits ONE tree per iteration for two classes (sigmoid of the raw score)
+        if binary:
+            A = 2           # multi:softprob form: class-0 trees are a single zero leaf, class-1 trees are HGB's,
+                            # softmax([0, raw]) = [1 - sigmoid(raw), sigmoid(raw)]
         feat, thr, left, right, dl, leaf, offs = [], [], [], [], [], [], [0]
         for it in range(len(preds)):
             for k in range(A):
-                nodes = preds[it][k].nodes
+                if binary and k == 0:
+                    feat.append(-1); thr.append(0.0); left.append(0); right.append(0); dl.append(0); leaf.append(np.float32(0))
+                    offs.append(len(feat))
+                    continue
+                nodes = preds[it][0 if binary else k].nodes
                 for nd in nodes:
                     if nd["is_leaf"]:
                         feat.append(-1); thr.append(0.0); left.append(0); right.append(0); dl.append(0)
@@ -77,6 +85,8 @@ class GBTForest:
                         dl.append(1 if nd["missing_go_to_left"] else 0); leaf.append(0.0)
                 offs.append(len(feat))
         base = np.asarray(hgb._baseline_prediction, dtype=np.float64).reshape(-1)[:A].astype(np.float32)
+        if binary:
+            base = np.array([0.0, base[0]], dtype=np.float32)
         return cls(A, n_features, feat, thr, left, right, dl, leaf, offs, base)
 
     @classmethod

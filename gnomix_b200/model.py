@@ -179,15 +179,30 @@ class Gnomix:
     # -- host-buffer fast path (include/gnx.h gnx_infer_host) ------------------
     def predict_host(self, X, want_proba=False, chunk_haps=0):
         """Streams a host int8 matrix through Base -> Smoother with overlapped copies.
-        Returns labels [N, W] int32 (and proba float32 if asked)."""
+        Returns labels [N, W] int32 (and proba float32 if asked).  Logistic base + tree smoother
+        without a calibrator only (what gnx_infer_host carries); anything else raises."""
         import ctypes as C
         from . import _lib
+        from .gbt import GBTForest
         _lib.require_gpu()
-        X = np.ascontiguousarray(X, dtype=np.int8) if not hasattr(X, "data_ptr") else X
+        if not isinstance(self.base, LogisticRegressionBase):
+            raise TypeError("predict_host needs a LogisticRegressionBase, not %s; use predict()" % type(self.base).__name__)
+        if not isinstance(getattr(self.smooth, "model", None), GBTForest):
+            raise TypeError("predict_host needs an XGB_Smoother holding a GBTForest; use predict()")
+        if getattr(self.smooth, "calibrate", False) and getattr(self.smooth, "calibrator", None) is not None:
+            raise NotImplementedError("predict_host does not apply the calibrator; use predict() / predict_proba()")
         if hasattr(X, "data_ptr"):
+            import torch
+            if X.is_cuda or X.dtype != torch.int8 or X.dim() != 2 or X.stride(1) != 1:
+                raise TypeError("predict_host takes a HOST int8 matrix [N, >=C] with unit column stride")
             N, ld, xp = X.shape[0], X.stride(0), X.data_ptr()
         else:
+            X = np.ascontiguousarray(X, dtype=np.int8)
+            if X.ndim != 2:
+                raise TypeError("predict_host takes a 2-D int8 matrix")
             N, ld, xp = X.shape[0], X.strides[0], X.ctypes.data
+        if X.shape[1] < self.C:
+            raise ValueError("X has %d columns, the model was built for C=%d SNPs" % (X.shape[1], self.C))
         labels = np.empty((N, self.W), dtype=np.int32)
         proba = np.empty((N, self.W, self.A), dtype=np.float32) if want_proba else None
         _lib.check(_lib.lib().gnx_infer_host(self.base.handle(), self.smooth.model.handle(self.smooth.S), xp, N, ld,

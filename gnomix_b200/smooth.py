@@ -80,6 +80,8 @@ class Smoother:
             _, label = self.calibrator.transform_device(proba, want_proba=False, want_label=True)
         else:
             _, label = self._device_smooth(B, want_proba=False, want_label=True)
+        if self.mode_filter:
+            label = mode_filter_device(label, self.mode_filter, self.A)
         if _is_torch(B) and B.is_cuda:
             return label
         torch.cuda.current_stream().synchronize()
@@ -95,6 +97,30 @@ class Smoother:
         accr = round_accr(accuracy_score(y.reshape(-1), y_pred.reshape(-1)))
         accr_bal = round_accr(balanced_accuracy_score(y.reshape(-1), y_pred.reshape(-1)))
         return accr, accr_bal
+
+
+def mode_filter_device(label, size, A):
+    """mode_filter of src/Smooth/utils.py:31-46 over the window axis of a cuda label tensor [N, W]: positions
+    ends <= i < W - ends (ends = size // 2) take the most frequent label of pred[i-ends : i+ends+1] when it is
+    unique among the most frequent ones, else keep the centre value; the borders are untouched (size 1 / True
+    is therefore a no-op, as in the reference).  Host-side glue in torch ops, not a hot kernel."""
+    import torch
+    ends = int(size) // 2
+    N, W = label.shape
+    if ends == 0 or W <= 2 * ends:
+        return label
+    lab = label.long()
+    oh = torch.nn.functional.one_hot(lab, A).to(torch.int32)
+    cs = torch.cat([torch.zeros((N, 1, A), dtype=torch.int32, device=label.device), oh.cumsum(1, dtype=torch.int32)], dim=1)
+    win = cs[:, 2 * ends + 1:] - cs[:, :W - 2 * ends]          # counts of window i-ends..i+ends for i = ends..W-ends-1
+    mx = win.max(dim=-1, keepdim=True).values
+    at_max = win == mx
+    unique = at_max.sum(-1) == 1
+    mode = at_max.to(torch.int8).argmax(-1)
+    out = label.clone()
+    mid = label[:, ends:W - ends]
+    out[:, ends:W - ends] = torch.where(unique, mode.to(label.dtype), mid)
+    return out
 
 
 def _train_calibrator(self, B, y, frac=0.05):
@@ -123,10 +149,12 @@ def host_slide_window(B, S):
 
 
 class XGB_Smoother(Smoother):
-    """src/Smooth/models.py:8-24.  `model` is a GBTForest (xgboost multi:softprob
-    semantics).  Training uses xgboost when it is importable and otherwise
-    scikit-learn's HistGradientBoostingClassifier with the reference's hyper-parameters
-    (100 rounds x A trees, depth 4, lr 0.1, lambda 1), exported to the same forest form."""
+    """src/Smooth/models.py:8-24.  `model` is a GBTForest (xgboost multi:softprob semantics); a model pickled by
+    the reference (an xgboost XGBClassifier) is converted on first use (pickle_compat).  Inference is the
+    accelerated path.  Training is NOT xgboost: `_fit` uses scikit-learn's HistGradientBoostingClassifier (255-bin
+    histogram splits) with the reference's hyper-parameters (100 rounds x A trees, depth 4, lr 0.1, lambda 1) on at
+    most `max_rows` (default 400 000) randomly chosen rows of the slid matrix, exported to the same forest form --
+    a stand-in so that train -> predict runs end to end, not a reproduction of xgboost's exact-split training."""
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -151,6 +179,9 @@ class XGB_Smoother(Smoother):
 
     def _device_smooth(self, B, want_proba=True, want_label=True):
         import torch
+        if self.model is not None and not isinstance(self.model, GBTForest):
+            from .pickle_compat import adopt_smoother_model
+            self.model = adopt_smoother_model(self.model, self.A, self.S)   # a foreign (reference-pickled) model
         assert isinstance(self.model, GBTForest), "XGB_Smoother has no trained forest"
         Bd = self._to_device_B(B, torch.float32)
         N, W, A = Bd.shape
@@ -209,6 +240,9 @@ class CRF_Smoother(Smoother):
 
     def _device_smooth(self, B, want_proba=True, want_label=True):
         import torch
+        if self.model is not None and not isinstance(self.model, CRFModel):
+            from .pickle_compat import adopt_smoother_model
+            self.model = adopt_smoother_model(self.model, self.A, self.S)
         assert isinstance(self.model, CRFModel), "CRF_Smoother has no trained model"
         Bd = self._to_device_B(B, torch.float64)
         N, W, A = Bd.shape

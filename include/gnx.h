@@ -107,6 +107,10 @@ void gnx_gbt_model_destroy(gnx_gbt_t* m);
  *   16 = tile kernel whatever the batch size (falls back to the row kernel when the shape does not fit).
  * Environment GNX_GBT_VARIANT=0|4|6 picks 10|14|16 at model-create time (profiling). */
 int gnx_gbt_set_kernel(gnx_gbt_t* m, int which);
+/* Profiling: with `on`, the tile path of gnx_gbt_smooth records CUDA events around its two launches (K4a rank pass,
+ * K4b tile walk) on the caller's stream; gnx_gbt_last_phase_ms waits for the last call and returns their durations. */
+int gnx_gbt_set_profile(gnx_gbt_t* m, int on);
+int gnx_gbt_last_phase_ms(const gnx_gbt_t* m, float* rank_ms, float* walk_ms);
 /* proba_dev [N,W,A] float32 and label_dev [N,W] int32; either may be NULL */
 int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, float* proba_dev,
                    int32_t* label_dev, void* stream);
