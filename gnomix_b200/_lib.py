@@ -49,6 +49,10 @@ _SIGS = {
     "gnx_calibrate": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp]),
     "gnx_gnofix_last_stats": (C.c_int, [c_vp]),
     "gnx_infer_host": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64]),
+    "gnx_infer_host_ex": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64]),
+    "gnx_vcf_to_haplotypes_packed": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, C.c_int]),
+    "gnx_host_alloc_pinned": (C.c_int, [C.POINTER(c_vp), c_i64]),
+    "gnx_host_free_pinned": (C.c_int, [c_vp]),
     "gnx_upload_haplotypes": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64]),
     "gnx_release_workspace": (C.c_int, []),
     "gnx_pack_rows_host": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, C.c_int, C.POINTER(C.c_int)]),
@@ -70,6 +74,12 @@ _SIGS = {
 }
 
 EXPORTS = tuple(_SIGS)
+
+
+class Pipeline(C.Structure):
+    """gnx_pipeline_t (include/gnx.h)."""
+    _fields_ = [("lr", c_vp), ("svc", c_vp), ("gbt", c_vp), ("crf", c_vp), ("cal", c_vp),
+                ("phase", C.c_int), ("max_it", C.c_int), ("x_packed", C.c_int)]
 
 
 def lib():

@@ -133,21 +133,21 @@ def run_inference(base_args, model, snp_level=False, bed_file_output=False, verb
     if verbose:
         print("Loading and processing query file...")
     vcf = gio.read_vcf(query_file, chm=chm, fields="*")
-    X_query, vcf_idx, fmt_idx = gio.vcf_to_npy(vcf, model.snp_pos, model.snp_ref, return_idx=True, verbose=verbose)
+    # gnomix.py:48-72 as ONE host-buffer pipeline: the genotype calls are gathered straight into 2-bit planes in
+    # pinned memory (a quarter of the int8 matrix's bytes cross PCIe, nothing is packed on the way) and
+    # Gnomix.predict_host streams them through Base -> [Gnofix] -> Smoother -> [Calibrator] with overlapped copies.
+    # Same labels / probabilities as the staged calls (tests/test_pipeline_gpu.py).
+    X_query, vcf_idx, fmt_idx = gio.vcf_to_packed(vcf, model.snp_pos, model.snp_ref, return_idx=True, verbose=verbose)
     if verbose:
         print("Inferring ancestry on query data...")
-    # gnomix.py:55-60 computes B on the host and hands it to the smoother / to phase(); here both stages run
-    # back to back on the device (Gnomix.predict_proba / phase with B=None): same values, no round trip of B
     if not base_args["phase"]:
-        y_proba = model.predict_proba(X_query)
-        y_pred = np.argmax(y_proba, axis=-1)
+        y_pred, y_proba = model.predict_host(X_query, want_proba=True)
     else:
-        X_phased, y_pred = model.phase(X_query)
+        y_pred, y_proba, X_phased = model.predict_host(X_query, want_proba=True, phase=True, want_phased=True)
         U = {"variants/REF": np.asarray(model.snp_ref)[fmt_idx],
              "variants/ALT": np.asarray(model.snp_alt)[fmt_idx].reshape(len(fmt_idx), 1)}
         vcf_phase = update_vcf(vcf, mask=vcf_idx, Updates=U)
         npy_to_vcf(vcf_phase, X_phased[:, fmt_idx], output_path + "/" + "query_file_phased", headers=read_headers(query_file))
-        y_proba = model.predict_proba(X_phased)
     if verbose:
         print("Saving results...")
     meta = pp.get_meta_data(chm, model.snp_pos, vcf["variants/POS"], model.W, model.M, gen_map_df)

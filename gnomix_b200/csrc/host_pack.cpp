@@ -134,6 +134,12 @@ static pack_row_fn choose_impl(int* which) {
     return pack_row_scalar;
 }
 
+unsigned pack_row_best(const int8_t* x, int64_t C, uint64_t* out, int64_t groups) {
+    static int which = 0;
+    static const pack_row_fn fn = choose_impl(&which);
+    return fn(x, C, out, groups);
+}
+
 // ------------------------------------------------------------------ worker pool
 // Persistent threads; run(n_items, fn) hands out item indices from an atomic counter and
 // returns when all are done.  One job at a time (gnx_infer_host holds the workspace lock).

@@ -15,6 +15,9 @@ namespace gnx {
 // *isa receives 0 scalar / 1 AVX2 / 2 AVX-512BW.
 int pack_rows(const int8_t* X, int64_t n, int64_t ldX, int64_t C, uint64_t* out, int64_t out_pitch_words, int threads,
               int* isa);
+// One row with the best instruction set of this CPU: x[0..C) -> out[0..2*groups) (groups >= ceil(C/64), the rest
+// zero); returns non-zero when a value was outside 0..3.
+unsigned pack_row_best(const int8_t* x, int64_t C, uint64_t* out, int64_t groups);
 int host_threads_default();
 // Runs fn(0) .. fn(items - 1) on the library's persistent host worker pool (`threads` <= 0: default count);
 // returns when all are done.  One job at a time.

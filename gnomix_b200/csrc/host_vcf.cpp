@@ -17,6 +17,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -446,6 +447,83 @@ int gnx_vcf_to_haplotypes(const int8_t* gt, int64_t R, int64_t S, const int64_t*
             for (int64_t h = 0; h < hn; h++) {
                 const int8_t v = src[h];
                 dst[h * ldX] = (v == 0 || v == 1) ? (int8_t)(sw ? 1 - v : v) : mf;
+            }
+        }
+    });
+    return 0;
+}
+
+/* vcf_to_npy straight into 2-bit planes (include/gnx.h).  Blocks of 64 haplotype rows; with ascending fmt_idx (the
+ * usual case: both position lists are sorted) a 64 x 4096 int8 tile that stays in L2 is filled like the int8 matrix
+ * would be and packed row by row with the pack kernels of host_pack.cpp; otherwise bits are set one by one. */
+int gnx_vcf_to_haplotypes_packed(const int8_t* gt, int64_t R, int64_t S, const int64_t* vcf_idx, const int64_t* fmt_idx,
+                                 const uint8_t* swap, int64_t n_idx, int64_t C, int miss_fill, uint64_t* packed, int64_t pitch_words,
+                                 int threads) {
+    if (R < 0 || S < 0 || n_idx < 0 || C < 0 || pitch_words < 2 * ((C + 63) / 64) || (n_idx > 0 && (!gt || !vcf_idx || !fmt_idx)) ||
+        (2 * S * C > 0 && !packed) || miss_fill < 0 || miss_fill > 3) {
+        gnx::set_error("gnx_vcf_to_haplotypes_packed: bad arguments");
+        return 2;
+    }
+    bool sorted = true;
+    for (int64_t k = 0; k < n_idx; k++) {
+        if (vcf_idx[k] < 0 || vcf_idx[k] >= R || fmt_idx[k] < 0 || fmt_idx[k] >= C) {
+            gnx::set_error("gnx_vcf_to_haplotypes_packed: index %lld out of range", (long long)k);
+            return 2;
+        }
+        if (k && fmt_idx[k] < fmt_idx[k - 1]) sorted = false;
+    }
+    const int64_t H = 2 * S;
+    const int64_t nblk = (H + 63) / 64;
+    const int8_t mf = (int8_t)miss_fill;
+    const int64_t groups = pitch_words / 2;
+    constexpr int64_t TC = 4096;
+    gnx::parallel_for(nblk, threads, [&](int64_t b) {
+        const int64_t h0 = b * 64, hn = std::min<int64_t>(64, H - h0);
+        if (sorted) {
+            std::vector<int8_t> tile((size_t)64 * TC);
+            int64_t kk = 0;
+            for (int64_t c0 = 0; c0 < C || c0 == 0; c0 += TC) {
+                const int64_t cn = std::min(TC, C - c0);
+                const bool last = c0 + TC >= C;
+                for (int64_t h = 0; h < hn; h++) memset(tile.data() + h * TC, mf, (size_t)std::max<int64_t>(cn, 0));
+                for (; kk < n_idx && fmt_idx[kk] < c0 + cn; kk++) {
+                    const int8_t* src = gt + vcf_idx[kk] * H + h0;
+                    int8_t* dst = tile.data() + (fmt_idx[kk] - c0);
+                    const bool sw = swap && swap[kk];
+                    for (int64_t h = 0; h < hn; h++) {
+                        const int8_t v = src[h];
+                        dst[h * TC] = (v == 0 || v == 1) ? (int8_t)(sw ? 1 - v : v) : mf;
+                    }
+                }
+                const int64_t g0 = c0 / 64;
+                const int64_t gn = last ? groups - g0 : TC / 64;
+                for (int64_t h = 0; h < hn; h++)
+                    gnx::pack_row_best(tile.data() + h * TC, std::max<int64_t>(cn, 0), packed + (h0 + h) * pitch_words + 2 * g0, gn);
+                if (last) break;
+            }
+            return;
+        }
+        const uint64_t f0 = (mf & 1) ? ~0ull : 0ull, f1 = (mf & 2) ? ~0ull : 0ull;
+        for (int64_t h = 0; h < hn; h++) {
+            uint64_t* row = packed + (h0 + h) * pitch_words;
+            for (int64_t g = 0; g < groups; g++) {
+                const int64_t left = C - 64 * g;
+                const uint64_t m = left >= 64 ? ~0ull : (left > 0 ? ((~0ull) >> (64 - left)) : 0ull);
+                row[2 * g] = f0 & m;
+                row[2 * g + 1] = f1 & m;
+            }
+        }
+        for (int64_t k = 0; k < n_idx; k++) {
+            const int8_t* src = gt + vcf_idx[k] * H + h0;
+            const int64_t g = fmt_idx[k] / 64;
+            const uint64_t bit = 1ull << (fmt_idx[k] % 64);
+            const bool sw = swap && swap[k];
+            for (int64_t h = 0; h < hn; h++) {
+                const int8_t v = src[h];
+                const unsigned o = (v == 0 || v == 1) ? (unsigned)(sw ? 1 - v : v) : (unsigned)mf;
+                uint64_t* w = packed + (h0 + h) * pitch_words + 2 * g;
+                w[0] = (w[0] & ~bit) | ((o & 1u) ? bit : 0ull);
+                w[1] = (w[1] & ~bit) | ((o & 2u) ? bit : 0ull);
             }
         }
     });

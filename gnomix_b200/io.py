@@ -188,6 +188,98 @@ def vcf_to_npy(vcf_data, snp_pos_fmt=None, snp_ref_fmt=None, miss_fill=2, return
     return mat
 
 
+class PackedHaplotypes:
+    """Haplotype matrix [N, C] with values 0..3 held as two bit planes per 64 SNPs (the gnx_pack_rows_host layout:
+    row = groups of {u64 bit 0, u64 bit 1}) in page-locked host memory: a quarter of the int8 matrix's bytes, and
+    what gnx_infer_host_ex takes as is (x_packed).  `words` is the uint64 view [N, pitch_words]."""
+
+    def __init__(self, N, C, pinned=True):
+        import ctypes as Ct
+        from . import _lib
+        self.N, self.C = int(N), int(C)
+        self.pitch_words = 2 * ((self.C + 127) // 128 * 2)      # 128-SNP multiple, as the device rows are pitched
+        nbytes = self.N * self.pitch_words * 8
+        self._ptr = None
+        if pinned and nbytes:
+            ptr = Ct.c_void_p()
+            _lib.check(_lib.lib().gnx_host_alloc_pinned(Ct.byref(ptr), nbytes), "gnx_host_alloc_pinned")
+            self._ptr = ptr
+            buf = (Ct.c_uint64 * (nbytes // 8)).from_address(ptr.value)
+            self.words = np.frombuffer(buf, dtype=np.uint64).reshape(self.N, self.pitch_words)
+        else:
+            self.words = np.zeros((self.N, self.pitch_words), dtype=np.uint64)
+
+    @property
+    def shape(self):
+        return (self.N, self.C)
+
+    def __len__(self):
+        return self.N
+
+    def __del__(self):
+        try:
+            if self._ptr is not None:
+                from . import _lib
+                self.words = None
+                _lib.lib().gnx_host_free_pinned(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+    @classmethod
+    def from_numpy(cls, X, pinned=True):
+        """int8 [N, C] with values in 0..3 -> packed (host cores, gnx_pack_rows_host)."""
+        import ctypes as Ct
+        from . import _lib
+        X = np.ascontiguousarray(X, dtype=np.int8)
+        out = cls(X.shape[0], X.shape[1], pinned=pinned)
+        bad = Ct.c_int(0)
+        rc = _lib.lib().gnx_pack_rows_host(X.ctypes.data, X.shape[0], X.strides[0] if X.shape[0] else X.shape[1], X.shape[1],
+                                           out.words.ctypes.data, out.pitch_words, 0, Ct.byref(bad))
+        if rc != 0 or bad.value:
+            raise ValueError("haplotype values outside 0..3 cannot be packed to 2 bits")
+        return out
+
+    def to_numpy(self):
+        """the int8 matrix back (numpy; for checks)."""
+        w = np.ascontiguousarray(self.words).reshape(self.N, -1, 2)
+        bits = np.unpackbits(w.view(np.uint8).reshape(self.N, -1, 2, 8), axis=-1, bitorder="little").reshape(self.N, -1, 2, 64)
+        X = (bits[:, :, 0, :] | (bits[:, :, 1, :] << 1)).reshape(self.N, -1).astype(np.int8)
+        return np.ascontiguousarray(X[:, :self.C])
+
+
+def vcf_to_packed(vcf_data, snp_pos_fmt=None, snp_ref_fmt=None, miss_fill=2, return_idx=False, verbose=True, pinned=True):
+    """vcf_to_npy (src/utils.py:104-159) with the result written straight into 2-bit planes in pinned memory
+    (gnx_vcf_to_haplotypes_packed): the matrix Gnomix.predict_host / the driver ship to the GPU without packing
+    or materialising int8.  `PackedHaplotypes.to_numpy()` equals vcf_to_npy's matrix."""
+    from . import _lib
+    gt = vcf_data["calldata/GT"]
+    assert isinstance(gt, np.ndarray) and gt.ndim == 3 and gt.shape[2] == 2, "calldata/GT must be [records, samples, 2]"
+    gt = np.ascontiguousarray(gt, dtype=np.int8)
+    R, S, _ = gt.shape
+    if snp_pos_fmt is not None:
+        fmt_idx, vcf_idx = snp_intersection(snp_pos_fmt, vcf_data["variants/POS"], verbose=verbose)
+        C = len(snp_pos_fmt)
+    else:
+        fmt_idx = vcf_idx = np.arange(R)
+        C = R
+    swap = None
+    if snp_ref_fmt is not None:
+        swap = np.asarray(vcf_data["variants/REF"])[vcf_idx] != np.asarray(snp_ref_fmt)[fmt_idx]
+        if swap.any() and verbose:
+            print("- Found ", int(swap.sum()), " (", round(np.mean(swap) * 100, 4), "%) different reference variants. Adjusting...", sep="")
+        swap = np.ascontiguousarray(swap, dtype=np.uint8)
+    vi = np.ascontiguousarray(vcf_idx, dtype=np.int64)
+    fi = np.ascontiguousarray(fmt_idx, dtype=np.int64)
+    out = PackedHaplotypes(2 * S, C, pinned=pinned)
+    _lib.check(_lib.lib().gnx_vcf_to_haplotypes_packed(gt.ctypes.data, R, S, vi.ctypes.data, fi.ctypes.data,
+                                                       None if swap is None else swap.ctypes.data, len(vi), C, int(miss_fill),
+                                                       out.words.ctypes.data, out.pitch_words, 0), "gnx_vcf_to_haplotypes_packed")
+    if return_idx:
+        return out, (vcf_idx if snp_pos_fmt is not None else np.arange(2 * S)), (fmt_idx if snp_pos_fmt is not None else np.arange(2 * S))
+    return out
+
+
 def vcf_to_npy_py(vcf_data, snp_pos_fmt=None, snp_ref_fmt=None, miss_fill=2, return_idx=False, verbose=True):
     """src/utils.py:104-159 in numpy, statement by statement."""
     data = vcf_data["calldata/GT"]

@@ -176,36 +176,78 @@ class Gnomix:
         from .gnofix import phase_all
         return phase_all(self, X, B=B, verbose=verbose, want_tracker=want_tracker)
 
-    # -- host-buffer fast path (include/gnx.h gnx_infer_host) ------------------
-    def predict_host(self, X, want_proba=False, chunk_haps=0):
-        """Streams a host int8 matrix through Base -> Smoother with overlapped copies.
-        Returns labels [N, W] int32 (and proba float32 if asked).  Logistic base + tree smoother
-        without a calibrator only (what gnx_infer_host carries); anything else raises."""
-        import ctypes as C
+    # -- host-buffer fast path (include/gnx.h gnx_infer_host_ex) ------------------
+    def predict_host(self, X, want_proba=False, chunk_haps=0, phase=False, want_phased=False):
+        """One call from a HOST haplotype matrix to labels: chunks stream through Base -> [Gnofix] -> Smoother ->
+        [Calibrator] on two device slots with the copies overlapped (gnomix.py:48-72 as one pipeline).
+        X: numpy / torch-CPU int8 [N, >=C] (pageable or pinned), or a `gnomix_b200.io.PackedHaplotypes`
+        (2-bit planes, e.g. from `vcf_to_packed`: a quarter of the bytes cross PCIe, no packing on the way).
+        Every plugin combination of the accelerated path is carried: logistic / CovRSK base, XGB / CRF smoother,
+        calibrator when `smooth.calibrate` is set, Gnofix with `phase=True` (tree smoother only).
+        Returns labels [N, W] int32; with want_proba also proba [N, W, A] (float32 for the tree smoother without
+        calibrator, float64 otherwise -- the reference's dtypes); with phase and want_phased also X_phased int8 [N, C]."""
+        import ctypes as Ct
         from . import _lib
         from .gbt import GBTForest
+        from .smooth import CRFModel
+        from .io import PackedHaplotypes
         _lib.require_gpu()
-        if not isinstance(self.base, LogisticRegressionBase):
-            raise TypeError("predict_host needs a LogisticRegressionBase, not %s; use predict()" % type(self.base).__name__)
-        if not isinstance(getattr(self.smooth, "model", None), GBTForest):
-            raise TypeError("predict_host needs an XGB_Smoother holding a GBTForest; use predict()")
-        if getattr(self.smooth, "calibrate", False) and getattr(self.smooth, "calibrator", None) is not None:
-            raise NotImplementedError("predict_host does not apply the calibrator; use predict() / predict_proba()")
-        if hasattr(X, "data_ptr"):
+        pipe = _lib.Pipeline()
+        if isinstance(self.base, LogisticRegressionBase):
+            pipe.lr = self.base.handle()
+        elif isinstance(self.base, CovRSKBase):
+            pipe.svc = self.base.handle()
+        else:
+            raise TypeError("predict_host: base %s is not on the accelerated path" % type(self.base).__name__)
+        sm = getattr(self.smooth, "model", None)
+        if sm is not None and not isinstance(sm, (GBTForest, CRFModel)):
+            from .pickle_compat import adopt_smoother_model
+            sm = self.smooth.model = adopt_smoother_model(sm, self.smooth.A, self.smooth.S)
+        if isinstance(sm, GBTForest):
+            pipe.gbt = sm.handle(self.smooth.S)
+        elif isinstance(sm, CRFModel):
+            pipe.crf = sm.handle()
+        else:
+            raise TypeError("predict_host: the smoother holds no trained forest / CRF")
+        cal = getattr(self.smooth, "calibrator", None)
+        use_cal = bool(getattr(self.smooth, "calibrate", False)) and cal is not None
+        if use_cal:
+            pipe.cal = cal.handle()
+        if getattr(self.smooth, "mode_filter", 0) not in (0, 1, False, True, None):
+            raise NotImplementedError("predict_host does not apply smooth.mode_filter; use predict()")
+        if phase:
+            assert getattr(self.smooth, "gnofix", False) and pipe.gbt, \
+                "Type of Smoother ({}) does not currently support re-phasing".format(self.smooth)
+            pipe.phase = 1
+        if isinstance(X, PackedHaplotypes):
+            N, Cx, ld, xp = X.N, X.C, X.pitch_words, X.words.ctypes.data
+            pipe.x_packed = 1
+            keep = X
+        elif hasattr(X, "data_ptr"):
             import torch
             if X.is_cuda or X.dtype != torch.int8 or X.dim() != 2 or X.stride(1) != 1:
                 raise TypeError("predict_host takes a HOST int8 matrix [N, >=C] with unit column stride")
-            N, ld, xp = X.shape[0], X.stride(0), X.data_ptr()
+            N, Cx, ld, xp = X.shape[0], X.shape[1], X.stride(0), X.data_ptr()
+            keep = X
         else:
-            X = np.ascontiguousarray(X, dtype=np.int8)
-            if X.ndim != 2:
+            keep = np.ascontiguousarray(X, dtype=np.int8)
+            if keep.ndim != 2:
                 raise TypeError("predict_host takes a 2-D int8 matrix")
-            N, ld, xp = X.shape[0], X.strides[0], X.ctypes.data
-        if X.shape[1] < self.C:
-            raise ValueError("X has %d columns, the model was built for C=%d SNPs" % (X.shape[1], self.C))
+            N, Cx, ld, xp = keep.shape[0], keep.shape[1], (keep.strides[0] if keep.shape[0] else keep.shape[1]), keep.ctypes.data
+        if Cx < self.C:
+            raise ValueError("X has %d columns, the model was built for C=%d SNPs" % (Cx, self.C))
+        if phase and N % 2:
+            N -= 1   # the reference's N // 2 reshape drops an odd trailing haplotype
         labels = np.empty((N, self.W), dtype=np.int32)
-        proba = np.empty((N, self.W, self.A), dtype=np.float32) if want_proba else None
-        _lib.check(_lib.lib().gnx_infer_host(self.base.handle(), self.smooth.model.handle(self.smooth.S), xp, N, ld,
-                                             proba.ctypes.data if want_proba else None, labels.ctypes.data, int(chunk_haps)),
-                   "gnx_infer_host")
-        return (labels, proba) if want_proba else labels
+        p_dtype = np.float64 if (pipe.crf or use_cal) else np.float32
+        proba = np.empty((N, self.W, self.A), dtype=p_dtype) if want_proba else None
+        xph = np.empty((N, self.C), dtype=np.int8) if (phase and want_phased) else None
+        _lib.check(_lib.lib().gnx_infer_host_ex(Ct.byref(pipe), xp, N, ld, proba.ctypes.data if want_proba else None, labels.ctypes.data,
+                                                xph.ctypes.data if xph is not None else None, int(chunk_haps)), "gnx_infer_host_ex")
+        del keep
+        out = (labels,)
+        if want_proba:
+            out += (proba,)
+        if xph is not None:
+            out += (xph,)
+        return out if len(out) > 1 else labels

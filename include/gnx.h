@@ -204,6 +204,33 @@ int gnx_calibrate(const gnx_cal_t* m, const void* proba_dev, int in_is_f32, int6
 int gnx_infer_host(const gnx_lr_t* lr, const gnx_gbt_t* gbt, const int8_t* X_host, int64_t N,
                    int64_t ldX, float* proba_host, int32_t* label_host, int64_t chunk_haps);
 
+/* The same host-buffer pipeline for every plugin combination of run_inference (gnomix.py:48-72):
+ *   base      exactly one of lr (LogisticRegressionBase) / svc (CovRSKBase);
+ *   smoother  exactly one of gbt (XGB_Smoother) / crf (CRF_Smoother);
+ *   cal       optional Calibrator applied to the smoother's probabilities (src/Smooth/smooth.py:48-52);
+ *   phase     != 0: Gnomix.phase (Gnofix, tree smoother only, N even): label_host receives gnofix's labels,
+ *             X_phased_host (int8 [N, C], may be NULL) the phased haplotypes, and proba_host -- when asked for --
+ *             the probabilities of the phased haplotypes run through the model again (gnomix.py:60-72);
+ *             max_it <= 0 means the reference's default 50;
+ *   x_packed  != 0: X_host holds rows already packed to 2-bit planes (the gnx_pack_rows_host layout, as
+ *             gnx_vcf_to_haplotypes_packed writes them) and ldX is the row pitch in 64-bit words: a quarter of
+ *             the bytes cross PCIe and no host core packs anything.
+ * Dtypes follow the reference's hand-offs: the CRF reads the base's float64 probabilities, the tree smoother
+ * float32 (a float64 string-kernel base output is rounded to float32, as slide_window's float32 matrix does);
+ * proba_host is float32 [N,W,A] for the tree smoother without calibrator, float64 otherwise. */
+typedef struct gnx_pipeline {
+    const gnx_lr_t* lr;
+    const gnx_svc_t* svc;
+    const gnx_gbt_t* gbt;
+    const gnx_crf_t* crf;
+    const gnx_cal_t* cal;
+    int phase;
+    int max_it;
+    int x_packed;
+} gnx_pipeline_t;
+int gnx_infer_host_ex(const gnx_pipeline_t* p, const void* X_host, int64_t N, int64_t ldX, void* proba_host,
+                      int32_t* label_host, int8_t* X_phased_host, int64_t chunk_haps);
+
 /* ---------------------------------------------------------------------------
  * Packed transfer of the haplotype matrix (the reference's int8 matrix,
  * src/utils.py:104-159, carries 2 bits per byte): gnx_infer_host packs on the host
@@ -281,6 +308,15 @@ int64_t gnx_vcf_strings(gnx_vcf_t* v, int field, char* buf, int64_t cap);
 int gnx_vcf_to_haplotypes(const int8_t* gt, int64_t R, int64_t S, const int64_t* vcf_idx,
                           const int64_t* fmt_idx, const uint8_t* swap, int64_t n_idx, int64_t C,
                           int miss_fill, int8_t* X, int64_t ldX, int threads);
+/* The same gather written straight into 2-bit planes (gnx_pack_rows_host layout, pitch_words >= 2*ceil(C/64)
+ * 64-bit words per haplotype row, `packed` preferably pinned): what gnx_infer_host_ex takes with x_packed, so
+ * the driver path VCF -> inference never materialises (or packs) the int8 matrix.  miss_fill must be in 0..3. */
+int gnx_vcf_to_haplotypes_packed(const int8_t* gt, int64_t R, int64_t S, const int64_t* vcf_idx,
+                                 const int64_t* fmt_idx, const uint8_t* swap, int64_t n_idx, int64_t C,
+                                 int miss_fill, uint64_t* packed, int64_t pitch_words, int threads);
+/* pinned (page-locked) host memory for callers without a CUDA runtime of their own (numpy drivers) */
+int gnx_host_alloc_pinned(void** out, int64_t bytes);
+int gnx_host_free_pinned(void* p);
 /* host threads the library uses (cores this process may run on, or GNX_HOST_THREADS) */
 int gnx_host_threads(void);
 

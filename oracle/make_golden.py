@@ -29,6 +29,7 @@ What each file pins (reference file:line):
 from __future__ import annotations
 
 import os
+import types
 import sys
 import warnings
 
@@ -342,6 +343,26 @@ def golden_calibrator(src):
     np.savez_compressed(os.path.join(OUT, "calibrator.npz"), **out)
 
 
+def golden_mode_filter(src):
+    """The reference's own mode_filter (src/Smooth/utils.py:31-46) on random label rows.  scipy >= 1.11 returns
+    scalars from stats.mode; the reference indexes `[0][0]` (scipy 1.5.3), so the call is given keepdims=True."""
+    from scipy import stats
+    su = sys.modules["src.Smooth.utils"]
+    orig = stats.mode
+    su.stats = types.SimpleNamespace(mode=lambda a: orig(a, keepdims=True))
+    rng = np.random.default_rng(11)
+    out = {}
+    for tag, (n, W, A, size) in {"a": (6, 40, 3, 5), "b": (4, 33, 7, 9), "c": (3, 20, 2, 4), "d": (2, 12, 4, 1), "e": (2, 7, 3, 11)}.items():
+        y = rng.integers(0, A, (n, W))
+        # runs of equal labels, as real predictions have them
+        y = np.where(rng.random((n, W)) < 0.6, np.roll(y, 1, axis=1), y)
+        got = np.apply_along_axis(func1d=su.mode_filter, axis=1, arr=y, size=size)
+        out["y_" + tag], out["size_" + tag], out["A_" + tag], out["out_" + tag] = y, size, A, got
+        print("mode_filter", tag, int((got != y).sum()), "changed")
+    su.stats = stats
+    np.savez_compressed(os.path.join(OUT, "mode_filter.npz"), **out)
+
+
 def main():
     from oracle import refimport
     src = refimport.import_reference()
@@ -356,6 +377,7 @@ def main():
     golden_vcf_to_npy(src)
     golden_calibrator(src)
     golden_lai_bed(src)
+    golden_mode_filter(src)
 
 
 if __name__ == "__main__":

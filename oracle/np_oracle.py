@@ -534,6 +534,24 @@ def calibrator_transform(proba, thresholds):
 # ----------------------------------------------------------------------------
 
 
+def mode_filter(pred: np.ndarray, size) -> np.ndarray:
+    """mode_filter + mode of src/Smooth/utils.py:31-46 for one label row: positions ends <= i < len - ends
+    (ends = size // 2) become the most frequent value of pred[i-ends : i+ends+1] when the smallest and the largest
+    most-frequent value coincide (scipy.stats.mode returns the smallest; the reference calls it on arr and -arr),
+    else the window's centre value; `range(len)[ends:-ends]` is empty for ends == 0, so size 1 / True changes nothing."""
+    pred = np.asarray(pred)
+    if not size:
+        return pred
+    out = np.copy(pred)
+    ends = int(size) // 2
+    for i in range(len(pred))[ends:-ends]:
+        arr = pred[i - ends:i + ends + 1]
+        vals, cnt = np.unique(arr, return_counts=True)
+        top = vals[cnt == cnt.max()]
+        out[i] = top[0] if len(top) == 1 else arr[len(arr) // 2]
+    return out
+
+
 def gnofix_default(X_m, X_p, B, S, predict_rows, smooth_predict, max_it=50):
     """gnofix(M,P,B,smoother) with every keyword at its default.
     predict_rows(rows[k,S*A]) -> proba[k,A]  (smoother.model.predict_proba)

@@ -314,3 +314,36 @@ def test_native_phased_vcf_writer_matches_python_loop(tmp_path):
         a = cli.npy_to_vcf(data, X, str(tmp_path / ("a%d" % R)), headers="##contig=<ID=22>\n")
         b = cli.npy_to_vcf_py(data, X, str(tmp_path / ("b%d" % R)), headers="##contig=<ID=22>\n")
         assert open(a, "rb").read() == open(b, "rb").read(), (R, n)
+
+
+def test_vcf_to_packed_equals_vcf_to_npy():
+    """gnx_vcf_to_haplotypes_packed writes the 2-bit planes of exactly the matrix vcf_to_npy returns (reference golden
+    included), for ascending and for shuffled index lists, every miss_fill in 0..3, C not a multiple of 64."""
+    from gnomix_b200 import _lib, io as gio
+    d = np.load(os.path.join(G, "vcf_to_npy.npz"))
+    vcf = {"calldata/GT": d["gt"], "variants/POS": d["vpos"], "variants/REF": d["vref"]}
+    P = gio.vcf_to_packed(vcf, d["model_pos"], d["model_ref"], verbose=False, pinned=False)
+    assert P.shape == d["X"].shape and np.array_equal(P.to_numpy(), d["X"])
+    assert np.array_equal(gio.PackedHaplotypes.from_numpy(d["X"], pinned=False).words, P.words)
+    rng = np.random.default_rng(3)
+    R, S, Cm = 700, 21, 1000 + 37
+    gt = rng.integers(-1, 4, (R, S, 2)).astype(np.int8)
+    for fill in (0, 1, 2, 3):
+        for shuffle in (False, True):
+            fmt = np.sort(rng.choice(Cm, 500, replace=False)).astype(np.int64)
+            vi = rng.choice(R, 500, replace=False).astype(np.int64)
+            if shuffle:
+                perm = rng.permutation(500)
+                fmt, vi = fmt[perm], vi[perm]
+            swap = (rng.random(500) < 0.3).astype(np.uint8)
+            X = np.empty((2 * S, Cm), np.int8)
+            _lib.check(_lib.lib().gnx_vcf_to_haplotypes(gt.ctypes.data, R, S, vi.ctypes.data, fmt.ctypes.data, swap.ctypes.data, 500, Cm, fill,
+                                                        X.ctypes.data, Cm, 3))
+            out = gio.PackedHaplotypes(2 * S, Cm, pinned=False)
+            out.words[:] = np.uint64(0xDEADBEEFDEADBEEF)
+            _lib.check(_lib.lib().gnx_vcf_to_haplotypes_packed(gt.ctypes.data, R, S, vi.ctypes.data, fmt.ctypes.data, swap.ctypes.data, 500, Cm,
+                                                               fill, out.words.ctypes.data, out.pitch_words, 3))
+            assert np.array_equal(out.to_numpy(), X), (fill, shuffle)
+            assert np.array_equal(out.words, gio.PackedHaplotypes.from_numpy(X, pinned=False).words), (fill, shuffle)
+    assert _lib.lib().gnx_vcf_to_haplotypes_packed(gt.ctypes.data, R, S, vi.ctypes.data, fmt.ctypes.data, None, 500, Cm, 7,
+                                                   out.words.ctypes.data, out.pitch_words, 1) != 0   # miss_fill must fit 2 bits

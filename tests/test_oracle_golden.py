@@ -196,3 +196,16 @@ def test_calibrator_restatement_matches_reference_calibrator():
     xp = np.sort(rng.random(40)); fp = np.sort(rng.random(40))
     x = np.concatenate([rng.random(500) * (xp[-1] - xp[0]) + xp[0], xp, [xp[0], xp[-1]]])
     assert np.array_equal(npo.np_interp_restated(x, xp, fp), np.interp(x, xp, fp))
+
+
+def test_mode_filter_restatement_and_plugin_against_reference():
+    """mode_filter of src/Smooth/utils.py:31-46 (the reference's own function, tests/golden/mode_filter.npz):
+    the oracle restatement and the plugin's torch statement (gnomix_b200.smooth.mode_filter_device, run on CPU
+    tensors here and on the device in tests/test_pipeline_gpu.py)."""
+    import torch
+    from gnomix_b200.smooth import mode_filter_device
+    d = np.load(os.path.join(G, "mode_filter.npz"))
+    for t in "abcde":
+        y, size, A = d["y_" + t], int(d["size_" + t]), int(d["A_" + t])
+        assert np.array_equal(np.stack([npo.mode_filter(r, size) for r in y]), d["out_" + t]), t
+        assert np.array_equal(mode_filter_device(torch.from_numpy(y.astype(np.int32)), size, A).numpy(), d["out_" + t]), t
