@@ -536,67 +536,84 @@ def run_ours(args):
         del mine, Bl, Ll, got
         barrier()
 
-    # ---- e2e: host buffers through gnx_infer_host --------------------------------
-    # 8 ranks of one box share the host: keep the pinned e2e batch at 10 GB per rank there
-    n_e2e = min(N, args.e2e_haps if world == 1 else min(args.e2e_haps, 8192))
-    Xh = torch.empty((n_e2e, ld), dtype=torch.int8, pin_memory=True)
-    Xh.copy_(X[:n_e2e])
-    Lh = torch.empty((n_e2e, W), dtype=torch.int32, pin_memory=True)
-    torch.cuda.synchronize()
-
-    def e2e_measure(fn, check):
-        fn()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            fn()
+    e2e = None
+    if not args.no_e2e:
+        # ---- e2e: host buffers through gnx_infer_host --------------------------------
+        # 8 ranks of one box share the host: keep the pinned e2e batch at 10 GB per rank there
+        n_e2e = min(N, args.e2e_haps if world == 1 else min(args.e2e_haps, 8192))
+        Xh = torch.empty((n_e2e, ld), dtype=torch.int8, pin_memory=True)
+        Xh.copy_(X[:n_e2e])
+        Lh = torch.empty((n_e2e, W), dtype=torch.int32, pin_memory=True)
         torch.cuda.synchronize()
-        e2e_s = maxr((time.perf_counter() - t0) / args.e2e_steps)
-        frac, h2d, d2h = C_.c_double(0), C_.c_int64(0), C_.c_int64(0)
-        lib.gnx_infer_host_last_transfer(C_.byref(frac), C_.byref(h2d), C_.byref(d2h))
-        return n_e2e * world / e2e_s, frac.value, h2d.value, d2h.value, check()
 
-    def c_abi():
-        _lib.check(lib.gnx_infer_host(hlr, hgbt, Xh.data_ptr(), n_e2e, ld, None, Lh.data_ptr(), 0), "gnx_infer_host")
+        def e2e_measure(fn, check, warm=1):
+            for _ in range(warm):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                fn()
+            torch.cuda.synchronize()
+            e2e_s = maxr((time.perf_counter() - t0) / args.e2e_steps)
+            frac, h2d, d2h = C_.c_double(0), C_.c_int64(0), C_.c_int64(0)
+            lib.gnx_infer_host_last_transfer(C_.byref(frac), C_.byref(h2d), C_.byref(d2h))
+            return n_e2e * world / e2e_s, frac.value, h2d.value, d2h.value, check()
 
-    same_as_resident = lambda: bool(torch.equal(Lh.cuda(), L[:n_e2e]))
-    # default path: part of every chunk crosses PCIe as 2-bit planes packed by the host cores
-    e2e_value, e2e_frac, e2e_h2d, e2e_d2h, labels_match = e2e_measure(c_abi, same_as_resident)
-    pk, h2dr = C_.c_double(0), C_.c_double(0)
-    lib.gnx_infer_host_rates(C_.byref(pk), C_.byref(h2dr))
-    # for comparison: the same call with packing switched off (raw int8 over PCIe)
-    os.environ["GNX_HOST_PACK"] = "0"
-    raw_value, _, raw_h2d, _, raw_match = e2e_measure(c_abi, same_as_resident)
-    del os.environ["GNX_HOST_PACK"]
-    labels_match = labels_match and raw_match
-    # the plugin call a gnomix user makes: Gnomix.predict_host on a numpy matrix in pageable memory
-    gm = Gnomix.__new__(Gnomix)
-    gm.C, gm.M, gm.A, gm.S, gm.W = C, M, A, S, W
-    gm.base, gm.smooth, gm.calibrate = base, smooth, False
-    Xnp = np.empty((n_e2e, C), dtype=np.int8)
-    Xnp[:] = Xh.numpy()[:, :C]
-    box = {}
+        def c_abi():
+            _lib.check(lib.gnx_infer_host(hlr, hgbt, Xh.data_ptr(), n_e2e, ld, None, Lh.data_ptr(), 0), "gnx_infer_host")
 
-    def plugin():
-        box["labels"] = gm.predict_host(Xnp)
+        same_as_resident = lambda: bool(torch.equal(Lh.cuda(), L[:n_e2e]))
+        # default path: part of every chunk crosses PCIe as 2-bit planes packed by the host cores
+        e2e_value, e2e_frac, e2e_h2d, e2e_d2h, labels_match = e2e_measure(c_abi, same_as_resident, warm=3)
+        pk, h2dr = C_.c_double(0), C_.c_double(0)
+        lib.gnx_infer_host_rates(C_.byref(pk), C_.byref(h2dr))
+        # for comparison: the same call with packing switched off (raw int8 over PCIe)
+        os.environ["GNX_HOST_PACK"] = "0"
+        raw_value, _, raw_h2d, _, raw_match = e2e_measure(c_abi, same_as_resident)
+        del os.environ["GNX_HOST_PACK"]
+        labels_match = labels_match and raw_match
+        # the plugin call a gnomix user makes: Gnomix.predict_host on a numpy matrix in pageable memory
+        gm = Gnomix.__new__(Gnomix)
+        gm.C, gm.M, gm.A, gm.S, gm.W = C, M, A, S, W
+        gm.base, gm.smooth, gm.calibrate = base, smooth, False
+        Xnp = np.empty((n_e2e, C), dtype=np.int8)
+        Xnp[:] = Xh.numpy()[:, :C]
+        box = {}
 
-    plug_value, _, plug_h2d, plug_d2h, plug_match = e2e_measure(
-        plugin, lambda: bool(np.array_equal(box["labels"], L[:n_e2e].cpu().numpy())))
-    del Xnp, box
-    # host rows that are ALREADY 2-bit planes (what gnomix_b200.io.vcf_to_packed hands the driver): a quarter of the
-    # bytes cross PCIe and no host core packs anything inside the timed region
-    from gnomix_b200.io import PackedHaplotypes
-    Pk = PackedHaplotypes.from_numpy(Xh.numpy()[:, :C])
-    pipe = _lib.Pipeline()
-    pipe.lr, pipe.gbt, pipe.x_packed = hlr, hgbt, 1
+        def plugin():
+            box["labels"] = gm.predict_host(Xnp)
 
-    def c_abi_packed():
-        _lib.check(lib.gnx_infer_host_ex(C_.byref(pipe), Pk.words.ctypes.data, n_e2e, Pk.pitch_words, None, Lh.data_ptr(), None, 0),
-                   "gnx_infer_host_ex")
+        plug_value, _, plug_h2d, plug_d2h, plug_match = e2e_measure(
+            plugin, lambda: bool(np.array_equal(box["labels"], L[:n_e2e].cpu().numpy())))
+        del Xnp, box
+        # host rows that are ALREADY 2-bit planes (what gnomix_b200.io.vcf_to_packed hands the driver): a quarter of the
+        # bytes cross PCIe and no host core packs anything inside the timed region
+        from gnomix_b200.io import PackedHaplotypes
+        Pk = PackedHaplotypes.from_numpy(Xh.numpy()[:, :C])
+        pipe = _lib.Pipeline()
+        pipe.lr, pipe.gbt, pipe.x_packed = hlr, hgbt, 1
 
-    Lh.zero_()
-    pk_value, _, pk_h2d, pk_d2h, pk_match = e2e_measure(c_abi_packed, same_as_resident)
-    del Pk
+        def c_abi_packed():
+            _lib.check(lib.gnx_infer_host_ex(C_.byref(pipe), Pk.words.ctypes.data, n_e2e, Pk.pitch_words, None, Lh.data_ptr(), None, 0),
+                       "gnx_infer_host_ex")
+
+        Lh.zero_()
+        pk_value, _, pk_h2d, pk_d2h, pk_match = e2e_measure(c_abi_packed, same_as_resident)
+        del Pk
+        e2e = {"value": e2e_value, "unit": "haplotypes/s", "h2d_bytes_per_step": int(e2e_h2d),
+               "d2h_bytes_per_step": int(e2e_d2h), "haplotypes_per_step": n_e2e,
+               "api": "gnx_infer_host (pinned host int8 in, int32 labels out)", "labels_match_resident_path": labels_match,
+               "packed_fraction_of_rows": e2e_frac, "host_threads": int(lib.gnx_host_threads()),
+               "calibrated_host_pack_gbs": pk.value, "calibrated_h2d_gbs": h2dr.value,
+               "unpacked": {"value": raw_value, "h2d_bytes_per_step": int(raw_h2d)},
+               "packed_input": {"value": pk_value, "api": "gnx_infer_host_ex(x_packed: pinned 2-bit-plane rows in, int32 labels out)",
+                                "h2d_bytes_per_step": int(pk_h2d), "d2h_bytes_per_step": int(pk_d2h),
+                                "labels_match_resident_path": pk_match,
+                                "note": "not the reference's int8 interface: the form the repo's own VCF reader (vcf_to_packed) "
+                                        "produces for the driver, reported beside the int8 number, not instead of it"},
+               "plugin_pageable": {"value": plug_value, "api": "Gnomix.predict_host(numpy int8 [N, C], pageable) -> numpy labels",
+                                   "h2d_bytes_per_step": int(plug_h2d), "d2h_bytes_per_step": int(plug_d2h),
+                                   "labels_match_resident_path": plug_match}}
 
     if rank != 0:
         if world > 1:
@@ -675,20 +692,7 @@ def run_ours(args):
                                % (C, M, W, A, S, N),
                    "forest": forest_kind, "l2": "inputs (%.1f GB/GPU) exceed L2, no flush needed" % (N * ld / 1e9),
                    "parallelism": "haplotype shards, one rank per GPU, no collective on the data path"},
-        "e2e": {"value": e2e_value, "unit": "haplotypes/s", "h2d_bytes_per_step": int(e2e_h2d),
-                "d2h_bytes_per_step": int(e2e_d2h), "haplotypes_per_step": n_e2e,
-                "api": "gnx_infer_host (pinned host int8 in, int32 labels out)", "labels_match_resident_path": labels_match,
-                "packed_fraction_of_rows": e2e_frac, "host_threads": int(lib.gnx_host_threads()),
-                "calibrated_host_pack_gbs": pk.value, "calibrated_h2d_gbs": h2dr.value,
-                "unpacked": {"value": raw_value, "h2d_bytes_per_step": int(raw_h2d)},
-                "packed_input": {"value": pk_value, "api": "gnx_infer_host_ex(x_packed: pinned 2-bit-plane rows in, int32 labels out)",
-                                 "h2d_bytes_per_step": int(pk_h2d), "d2h_bytes_per_step": int(pk_d2h),
-                                 "labels_match_resident_path": pk_match,
-                                 "note": "not the reference's int8 interface: the form the repo's own VCF reader (vcf_to_packed) "
-                                         "produces for the driver, reported beside the int8 number, not instead of it"},
-                "plugin_pageable": {"value": plug_value, "api": "Gnomix.predict_host(numpy int8 [N, C], pageable) -> numpy labels",
-                                    "h2d_bytes_per_step": int(plug_h2d), "d2h_bytes_per_step": int(plug_d2h),
-                                    "labels_match_resident_path": plug_match}},
+        "e2e": e2e,
         "strong": strong,
         "gpu_launches": 3 * args.steps,
         "roofline": roof_k4 if dom.startswith("K4") else roof_k1,
@@ -734,6 +738,7 @@ def main():
     ap.add_argument("--covrsk-haps", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -350,7 +350,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
                 m->h_tiletop->q[t] = make_uint4(t0, conv(top[(size_t)t * 4 + 1]), conv(top[(size_t)t * 4 + 2]), t0 & 0x1ff80u);
                 for (int k = 0; k < 3; k++) m->h_tiletop3->w[3 * t + k] = conv(top[(size_t)t * 4 + k]);
             }
-            if (gbt_rank_lut_build(m->d.thr_table, tab.data(), K, &m->rank_tmin, &m->rank_tmax, &m->rank_scale, &m->rank_lut)) {
+            if (gbt_rank_lut_build(tab.data(), K, &m->rank_tmin, &m->rank_tmax, &m->rank_kmin, &m->rank_shift, &m->rank_lut)) {
                 gnx_gbt_model_destroy(m);
                 return 1;
             }

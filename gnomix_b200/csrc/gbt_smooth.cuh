@@ -251,7 +251,9 @@ struct gnx_gbt {
     gnx::GbtTopC* h_tiletop3;     // 3 words per tree (GNX_GBT_TOPW=3)
     int tile_top_words;
     uint32_t* rank_lut;           // [GBT_RANK_CELLS] first threshold of the cell | thresholds in it << 16
-    float rank_tmin, rank_tmax, rank_scale;
+    float rank_tmin, rank_tmax;
+    uint32_t rank_kmin;           // key of the smallest threshold, cell = (key(x) - rank_kmin) >> rank_shift
+    int rank_shift;
     int profile;                  // gnx_gbt_set_profile: record events around the rank pass and the walk
     cudaEvent_t ev[3];
     const unsigned char* tile_forest;
@@ -262,7 +264,7 @@ struct gnx_gbt {
 namespace gnx {
 // gbt_tile.cu: K4a (rank transform into hap-block-interleaved u16 tiles) + K4b (tile walk).  Returns 0 when it ran,
 // -1 when the shape does not fit the tile kernel (caller falls back to the row kernel), > 0 on error.
-int gbt_rank_lut_build(const float* tab_dev, const float* tab_host, int K, float* tmin, float* tmax, float* scale, uint32_t** lut_dev);
+int gbt_rank_lut_build(const float* tab_host, int K, float* tmin, float* tmax, uint32_t* kmin, int* shift, uint32_t** lut_dev);
 int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, float* proba_dev, int32_t* label_dev,
                     cudaStream_t st);
 }  // namespace gnx

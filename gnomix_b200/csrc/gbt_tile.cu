@@ -19,6 +19,8 @@
 //     shared and there are 2 * A independent dependency chains in flight.
 // K4a turns the float32 base probabilities into their exact ranks (u16) once, written in the order the
 // tiles are staged in: R2[haplotype block][padded slot][class][32 lanes], reflect padding materialised.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -44,29 +46,33 @@ constexpr uint32_t TILE_FMASK = 0x1ff80u;   // feature << 7 field of a node word
 // B f32 [N, W, A] -> R2 u16 [ceil(N/32)][Wp = W + S - 1][A][32]; NaN -> 0xFFFF, lanes beyond N -> 0.
 // rank(x) = #{i : tab[i] <= x}, exactly.  A binary search over the shared-memory table probes, at every level whose
 // step is a multiple of 32 words, ONE bank for the whole warp (measured: 139 wavefronts per warp and element, 9 ms at
-// 50 000 haplotypes).  Instead the threshold range [tab[0], tab[K-1]) is cut into GBT_RANK_CELLS equal cells:
-// cell(x) is a monotone function of x, so every threshold in a lower cell is < x and every threshold in a higher
-// cell is > x, and only the (on average ~1) thresholds sharing x's cell are compared.  lut[c] = first threshold of
-// cell c | number of thresholds in it << 16, built at model-create time from cell() evaluated ON THE DEVICE for
-// every threshold (the same instruction sequence as here, so host and device never disagree on a cell boundary).
-__device__ __forceinline__ int gbt_rank_cell(float x, float tmin, float scale) {
-    const int c = __float2int_rz(__fmul_rn(__fsub_rn(x, tmin), scale));
-    return min(max(c, 0), GBT_RANK_CELLS - 1);
-}
-
-__global__ void gbt_rank_cells_kernel(const float* __restrict__ tab, int K, float tmin, float scale, int* __restrict__ cell) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < K) cell[i] = gbt_rank_cell(tab[i], tmin, scale);
+// 50 000 haplotypes).  Instead the ordered key space of float32 between tab[0] and tab[K-1] is cut into
+// GBT_RANK_CELLS cells: key(x) = the usual order-preserving integer image of a float (sign bit flipped for positive
+// values, all bits for negative ones; -0 canonicalised to +0 first), cell(x) = (key(x) - key(tab[0])) >> shift.
+// cell() is monotone in x, so every threshold in a lower cell is <= x ... < and every threshold in a higher cell is
+// > x: only the thresholds sharing x's cell are compared.  Cells are log-spaced like floats themselves, so the
+// thresholds crowded near 0 (base probabilities) spread over many cells where equal-width cells (first version:
+// 3.8 ms, long binary searches inside a few crowded cells under divergence) put them in a handful.
+// lut[c] = first threshold of cell c | number of thresholds in it << 16, built on the host with the same integer key.
+__host__ __device__ __forceinline__ uint32_t gbt_float_key(float x) {
+    x = x + 0.0f;   // -0 -> +0 (exact); NaN never reaches here
+#ifdef __CUDA_ARCH__
+    const uint32_t b = __float_as_uint(x);
+#else
+    uint32_t b;
+    memcpy(&b, &x, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
 __device__ __forceinline__ uint32_t gbt_rank_lut(const float* __restrict__ tab, const uint32_t* __restrict__ lut, int K, float tmin,
-                                                 float tmax, float scale, float x) {
+                                                 float tmax, uint32_t kmin, int shift, float x) {
     if (x != x) return 0xFFFFu;
     if (K == 0 || x < tmin) return 0u;
     if (x >= tmax) return (uint32_t)K;
-    const uint32_t e = lut[gbt_rank_cell(x, tmin, scale)];
+    const uint32_t e = lut[min((gbt_float_key(x) - kmin) >> shift, (uint32_t)(GBT_RANK_CELLS - 1))];
     int lo = (int)(e & 0xffffu), n = (int)(e >> 16);
-    if (n <= 4) {
+    if (n <= 8) {
         while (n > 0 && tab[lo] <= x) { lo++; n--; }
         return (uint32_t)lo;
     }
@@ -78,68 +84,84 @@ __device__ __forceinline__ uint32_t gbt_rank_lut(const float* __restrict__ tab, 
     return (uint32_t)lo;
 }
 
-// lane = haplotype of the block (the 64-byte rows of R2 are written whole); a warp owns a run of consecutive
-// elements, so the 32-byte sectors its lanes read (one per haplotype) are reused from L1 for the next 7 elements.
-constexpr int RANK_RUN = 64;
-__global__ void __launch_bounds__(256)
-gbt_rank_tile_kernel(const float* __restrict__ thr, const uint32_t* __restrict__ lut_g, int K, float tmin, float tmax, float scale,
+// One CTA pass = one tile of 32 haplotypes x RANK_EL padded elements.  Reads are coalesced along a haplotype's row
+// (warp = haplotype, lane = element, 8 independent loads in flight per lane), ranks are transposed through shared
+// memory, and the tile leaves as ONE contiguous 16 KB run of R2 (16 bytes per thread).
+constexpr int RANK_EL = 256;
+constexpr int RANK_THREADS = 1024;
+constexpr int RANK_TS = 34;   // u16 per tile row (32 haplotypes + 2: rows 17 words apart, conflict-free transposition)
+__global__ void __launch_bounds__(RANK_THREADS, 2)
+gbt_rank_tile_kernel(const float* __restrict__ thr, const uint32_t* __restrict__ lut_g, int K, float tmin, float tmax, uint32_t kmin, int shift,
                      int table_in_smem, const float* __restrict__ B, int64_t N, int W, int A, int S, uint16_t* __restrict__ R2) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t* lut = lut_g;
+    uint16_t* tile = reinterpret_cast<uint16_t*>(smem);
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem + RANK_EL * RANK_TS * 2);
     const float* tab = thr;
-    {
-        uint32_t* l = reinterpret_cast<uint32_t*>(smem);
-        for (int i = threadIdx.x; i < GBT_RANK_CELLS; i += blockDim.x) l[i] = __ldg(lut_g + i);
-        lut = l;
-        if (table_in_smem) {
-            float* t = reinterpret_cast<float*>(smem + GBT_RANK_CELLS * 4);
-            for (int i = threadIdx.x; i < K; i += blockDim.x) t[i] = __ldg(thr + i);
-            tab = t;
-        }
-        __syncthreads();
+    for (int i = threadIdx.x; i < GBT_RANK_CELLS; i += blockDim.x) lut[i] = __ldg(lut_g + i);
+    if (table_in_smem) {
+        float* t = reinterpret_cast<float*>(smem + RANK_EL * RANK_TS * 2 + GBT_RANK_CELLS * 4);
+        for (int i = threadIdx.x; i < K; i += blockDim.x) t[i] = __ldg(thr + i);
+        tab = t;
     }
     const int pad = (S + 1) / 2, Wp = W + S - 1, E = Wp * A;
-    const int runs = (E + RANK_RUN - 1) / RANK_RUN;
+    const int runs = (E + RANK_EL - 1) / RANK_EL;
     const int64_t nhb = (N + 31) / 32, items = nhb * runs;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t it = warp0; it < items; it += nwarps) {
+    const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;   // h = haplotype of the block this warp reads
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
         const int64_t hb = it / runs;
-        const int e0 = (int)(it - hb * runs) * RANK_RUN, e1 = min(e0 + RANK_RUN, E);
-        const int64_t n = hb * 32 + lane;
+        const int e0 = (int)(it - hb * runs) * RANK_EL;
+        const int64_t n = hb * 32 + h;
         const float* bn = B + n * (int64_t)W * A;
-        uint16_t* out = R2 + (hb * E + e0) * 32 + lane;
-        int j = e0 / A, a = e0 - j * A;
-        for (int e = e0; e < e1; e++) {
+        float x[RANK_EL / 32];
+#pragma unroll
+        for (int q = 0; q < RANK_EL / 32; q++) {
+            const int e = e0 + q * 32 + lane;
+            x[q] = 0.f;
+            if (n < N && e < E) {
+                const int j = e / A, a = e - j * A;
+                x[q] = __ldg(bn + (int64_t)spad_to_orig(j, W, pad) * A + a);
+            }
+        }
+        __syncthreads();   // the previous tile has left shared memory (and, first time round, lut / tab are in place)
+#pragma unroll
+        for (int q = 0; q < RANK_EL / 32; q++) {
+            const int e = e0 + q * 32 + lane;
             uint16_t r = 0;
-            if (n < N) r = (uint16_t)gbt_rank_lut(tab, lut, K, tmin, tmax, scale, __ldg(bn + (int64_t)spad_to_orig(j, W, pad) * A + a));
-            *out = r;
-            out += 32;
-            if (++a == A) { a = 0; j++; }
+            if (n < N && e < E) r = (uint16_t)gbt_rank_lut(tab, lut, K, tmin, tmax, kmin, shift, x[q]);
+            tile[(q * 32 + lane) * RANK_TS + h] = r;
+        }
+        __syncthreads();
+        {
+            // thread t: element t / 4 of the tile, haplotypes 8 * (t % 4) .. + 7 -> 16 bytes
+            const int el = threadIdx.x >> 2, part = threadIdx.x & 3;
+            if (e0 + el < E) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(tile + el * RANK_TS + part * 8);
+                uint4 v;
+                v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+                *reinterpret_cast<uint4*>(R2 + ((hb * E + e0 + el) * 32 + part * 8)) = v;
+            }
         }
     }
 }
 
 // model-create half of the rank pass: the cell table (see above).  Returns 0 / non-zero like the C ABI.
-int gbt_rank_lut_build(const float* tab_dev, const float* tab_host, int K, float* tmin, float* tmax, float* scale, uint32_t** lut_dev) {
+int gbt_rank_lut_build(const float* tab_host, int K, float* tmin, float* tmax, uint32_t* kmin, int* shift, uint32_t** lut_dev) {
     std::vector<uint32_t> lut(GBT_RANK_CELLS, 0u);
     *tmin = K ? tab_host[0] : 0.f;
     *tmax = K ? tab_host[K - 1] : 0.f;
-    const float span = *tmax - *tmin;
-    *scale = (K > 1 && span > 0.f && span < INFINITY) ? (float)GBT_RANK_CELLS / span : 0.f;
-    if (!(*scale == *scale) || *scale == INFINITY) *scale = 0.f;   // every x then lands in cell 0: still exact, just slower
+    *kmin = K ? gbt_float_key(*tmin) : 0u;
+    *shift = 0;
     if (K > 0) {
-        int* cell_dev = nullptr;
-        GNX_CUDA(cudaMalloc((void**)&cell_dev, (size_t)K * sizeof(int)));
-        gbt_rank_cells_kernel<<<(K + 255) / 256, 256>>>(tab_dev, K, *tmin, *scale, cell_dev);
-        std::vector<int> cell(K);
-        const cudaError_t e = cudaMemcpy(cell.data(), cell_dev, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost);
-        cudaFree(cell_dev);
-        GNX_CUDA(e);
+        const uint32_t span = gbt_float_key(*tmax) - *kmin;
+        while ((span >> *shift) >= (uint32_t)GBT_RANK_CELLS) (*shift)++;
         std::vector<uint32_t> cnt(GBT_RANK_CELLS, 0u);
+        uint32_t prev = 0;
         for (int i = 0; i < K; i++) {
-            GNX_REQUIRE(cell[i] >= 0 && cell[i] < GBT_RANK_CELLS && (i == 0 || cell[i] >= cell[i - 1]), "gnx_gbt_model_create: rank cells are not monotone");
-            cnt[cell[i]]++;
+            GNX_REQUIRE(tab_host[i] == tab_host[i] && (i == 0 || tab_host[i] >= tab_host[i - 1]), "gnx_gbt_model_create: threshold table is not sorted");
+            const uint32_t c = std::min<uint32_t>((gbt_float_key(tab_host[i]) - *kmin) >> *shift, GBT_RANK_CELLS - 1);
+            GNX_REQUIRE(c >= prev, "gnx_gbt_model_create: rank cells are not monotone");
+            prev = c;
+            cnt[c]++;
         }
         uint32_t start = 0;
         for (int c = 0; c < GBT_RANK_CELLS; c++) {
@@ -337,14 +359,14 @@ int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, floa
     GNX_CUDA(cudaMallocAsync((void**)&R2, (size_t)nhb * Wp * A * 32 * sizeof(uint16_t), st));
     if (m->profile) GNX_CUDA(cudaEventRecord(m->ev[0], st));
     {
-        const int in_smem = (size_t)m->d.K * 4 <= 96 * 1024;
-        const size_t rsm = GBT_RANK_CELLS * 4 + (in_smem ? (size_t)m->d.K * 4 : 0);
-        GNX_CUDA(cudaFuncSetAttribute(gbt_rank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GBT_RANK_CELLS * 4 + 96 * 1024)));
-        const int64_t items = nhb * ceil_div((int64_t)Wp * A, RANK_RUN);
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / rsm));
-        const int grid = (int)std::min<int64_t>(ceil_div(items, 8), (int64_t)sm_count() * per_sm);
-        gbt_rank_tile_kernel<<<grid, 256, rsm, st>>>(m->d.thr_table, m->rank_lut, m->d.K, m->rank_tmin, m->rank_tmax, m->rank_scale, in_smem,
-                                                     B_dev, N, W, A, S, R2);
+        const size_t fixed = (size_t)RANK_EL * RANK_TS * 2 + GBT_RANK_CELLS * 4;
+        const int in_smem = fixed + (size_t)m->d.K * 4 <= 110 * 1024;   // two CTAs per SM
+        const size_t rsm = fixed + (in_smem ? (size_t)m->d.K * 4 : 0);
+        GNX_CUDA(cudaFuncSetAttribute(gbt_rank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024)));
+        const int64_t items = nhb * ceil_div((int64_t)Wp * A, RANK_EL);
+        const int grid = (int)std::min<int64_t>(items, (int64_t)sm_count() * 2);
+        gbt_rank_tile_kernel<<<grid, RANK_THREADS, rsm, st>>>(m->d.thr_table, m->rank_lut, m->d.K, m->rank_tmin, m->rank_tmax, m->rank_kmin,
+                                                              m->rank_shift, in_smem, B_dev, N, W, A, S, R2);
         GNX_CUDA(cudaGetLastError());
     }
     if (m->profile) GNX_CUDA(cudaEventRecord(m->ev[1], st));
