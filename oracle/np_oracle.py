@@ -211,6 +211,11 @@ def expf_cr(x: np.ndarray) -> np.ndarray:
 
 
 def gbt_margins(model: GBTModel, rows: np.ndarray) -> np.ndarray:
+    """xgboost 1.1.1 src/predictor/cpu_predictor.cc, restated (PARITY UNPINNED until tests/golden/pin_xgboost.npz exists):
+    `PredValue`: psum = 0 (bst_float), for the trees of output group gid in tree order: `tid = tree.GetLeafIndex(feats)`
+    (include/xgboost/tree_model.h `GetNext`: missing -> cdefault(), else `fvalue < split_cond` -> left),
+    psum += leaf value; `PredictBatchKernel` then does `preds[ridx * num_group + gid] += psum` where preds was
+    initialised to base_margin (learner base_score for every class): float32 throughout, base added last."""
     rows = np.asarray(rows, dtype=np.float32)
     k = rows.shape[0]
     psum = np.zeros((k, model.A), dtype=np.float32)
@@ -229,6 +234,9 @@ def gbt_margins(model: GBTModel, rows: np.ndarray) -> np.ndarray:
 
 
 def softmax_xgb(m: np.ndarray) -> np.ndarray:
+    """xgboost 1.1.1 src/common/math.h `Softmax(begin, end)` as called by src/objective/multiclass_obj.cu
+    `SoftmaxMultiClassObj::Transform` (multi:softprob): wmax = max; `double wsum = 0; for each: *i = expf(*i - wmax);
+    wsum += *i;` then `*i /= static_cast<float>(wsum)` -- float32 exp, float64 running sum, float32 division."""
     m = np.asarray(m, dtype=np.float32)
     wmax = m.max(axis=1, keepdims=True)
     e = expf_cr((m - wmax).astype(np.float32))
@@ -260,7 +268,13 @@ def xgb_smooth(model: GBTModel, B: np.ndarray, S: int):
 
 
 def crf_marginals(Bn: np.ndarray, state_w: np.ndarray, trans_w: np.ndarray) -> np.ndarray:
-    """One sequence Bn [W, A] (float64) -> marginals [W, L] float64."""
+    """One sequence Bn [W, A] (float64) -> marginals [W, L] float64.
+    CRFsuite 0.12 lib/crf/src/crf1d_context.c, restated (PARITY UNPINNED until tests/golden/pin_crfsuite.npz exists):
+    `crf1dc_exp_state / crf1dc_exp_transition` (exp of the score tables), `crf1dc_alpha_score` (alpha[0] = exp_state[0];
+    alpha[t] = (sum_i alpha[t-1][i] * exp_trans[i]) * exp_state[t]; each row scaled by 1 / its sum, scale kept),
+    `crf1dc_beta_score` (beta[T-1] = scale[T-1]; beta[t][i] = sum_j exp_trans[i][j] * (beta[t+1][j] * exp_state[t+1][j]),
+    times scale[t]), `crf1dc_marginal_point` (alpha[t][l] * beta[t][l] / scale[t]); state score of label y at t =
+    sum over the item's attributes of value * weight (crf1d_tag.c `crf1dt_state_score`)."""
     T, A = Bn.shape
     L = state_w.shape[1]
     state = np.zeros((T, L))
