@@ -297,6 +297,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->h_tiletop = nullptr;
     m->h_tiletop3 = nullptr;
     m->rank_lut = nullptr;
+    m->rank_tab = nullptr;
     m->profile = 0;
     m->ev[0] = m->ev[1] = m->ev[2] = nullptr;
     m->tile_top_words = 4;
@@ -350,7 +351,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
                 m->h_tiletop->q[t] = make_uint4(t0, conv(top[(size_t)t * 4 + 1]), conv(top[(size_t)t * 4 + 2]), t0 & 0x1ff80u);
                 for (int k = 0; k < 3; k++) m->h_tiletop3->w[3 * t + k] = conv(top[(size_t)t * 4 + k]);
             }
-            if (gbt_rank_lut_build(tab.data(), K, &m->rank_tmin, &m->rank_tmax, &m->rank_kmin, &m->rank_shift, &m->rank_lut)) {
+            if (gbt_rank_lut_build(tab.data(), K, &m->rank_cells, &m->rank_lut, &m->rank_tab)) {
                 gnx_gbt_model_destroy(m);
                 return 1;
             }
@@ -378,6 +379,7 @@ void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     if (m->tile_forest) cudaFree(const_cast<unsigned char*>(m->tile_forest));
     if (m->block_forest) cudaFree(const_cast<unsigned char*>(m->block_forest));
     if (m->rank_lut) cudaFree(m->rank_lut);
+    if (m->rank_tab) cudaFree(m->rank_tab);
     for (int i = 0; i < 3; i++)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m->h_tiletop;

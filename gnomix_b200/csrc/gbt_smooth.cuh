@@ -232,6 +232,13 @@ __device__ __forceinline__ float gbt_rank_tree(const unsigned char* __restrict__
 }
 #endif  // __CUDACC__
 
+// monotone cell function of the tile kernel's rank pass (gbt_tile.cu)
+struct GbtRankCells {
+    float tmin, tmax;
+    uint32_t kminA, kminB;   // key(tab[0]), key(1 - tab[K-1])
+    int shiftA, shiftB;
+};
+
 }  // namespace gnx
 
 struct gnx_gbt {
@@ -251,9 +258,8 @@ struct gnx_gbt {
     gnx::GbtTopC* h_tiletop3;     // 3 words per tree (GNX_GBT_TOPW=3)
     int tile_top_words;
     uint32_t* rank_lut;           // [GBT_RANK_CELLS] first threshold of the cell | thresholds in it << 16
-    float rank_tmin, rank_tmax;
-    uint32_t rank_kmin;           // key of the smallest threshold, cell = (key(x) - rank_kmin) >> rank_shift
-    int rank_shift;
+    gnx::GbtRankCells rank_cells; // monotone cell function of the rank pass (gbt_tile.cu)
+    float* rank_tab;              // the threshold table followed by NaN sentinels
     int profile;                  // gnx_gbt_set_profile: record events around the rank pass and the walk
     cudaEvent_t ev[3];
     const unsigned char* tile_forest;
@@ -264,7 +270,7 @@ struct gnx_gbt {
 namespace gnx {
 // gbt_tile.cu: K4a (rank transform into hap-block-interleaved u16 tiles) + K4b (tile walk).  Returns 0 when it ran,
 // -1 when the shape does not fit the tile kernel (caller falls back to the row kernel), > 0 on error.
-int gbt_rank_lut_build(const float* tab_host, int K, float* tmin, float* tmax, uint32_t* kmin, int* shift, uint32_t** lut_dev);
+int gbt_rank_lut_build(const float* tab_host, int K, GbtRankCells* cells, uint32_t** lut_dev, float** tab_dev);
 int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, float* proba_dev, int32_t* label_dev,
                     cudaStream_t st);
 }  // namespace gnx

@@ -19,6 +19,7 @@
 //     shared and there are 2 * A independent dependency chains in flight.
 // K4a turns the float32 base probabilities into their exact ranks (u16) once, written in the order the
 // tiles are staged in: R2[haplotype block][padded slot][class][32 lanes], reflect padding materialised.
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -46,14 +47,17 @@ constexpr uint32_t TILE_FMASK = 0x1ff80u;   // feature << 7 field of a node word
 // B f32 [N, W, A] -> R2 u16 [ceil(N/32)][Wp = W + S - 1][A][32]; NaN -> 0xFFFF, lanes beyond N -> 0.
 // rank(x) = #{i : tab[i] <= x}, exactly.  A binary search over the shared-memory table probes, at every level whose
 // step is a multiple of 32 words, ONE bank for the whole warp (measured: 139 wavefronts per warp and element, 9 ms at
-// 50 000 haplotypes).  Instead the ordered key space of float32 between tab[0] and tab[K-1] is cut into
-// GBT_RANK_CELLS cells: key(x) = the usual order-preserving integer image of a float (sign bit flipped for positive
-// values, all bits for negative ones; -0 canonicalised to +0 first), cell(x) = (key(x) - key(tab[0])) >> shift.
-// cell() is monotone in x, so every threshold in a lower cell is <= x ... < and every threshold in a higher cell is
-// > x: only the thresholds sharing x's cell are compared.  Cells are log-spaced like floats themselves, so the
-// thresholds crowded near 0 (base probabilities) spread over many cells where equal-width cells (first version:
-// 3.8 ms, long binary searches inside a few crowded cells under divergence) put them in a handful.
-// lut[c] = first threshold of cell c | number of thresholds in it << 16, built on the host with the same integer key.
+// 50 000 haplotypes).  Instead x is hashed by a MONOTONE cell function and only the thresholds sharing x's cell are
+// compared: every threshold in a lower cell is <= ... < x's cell, every threshold in a higher cell is > x.
+//   key(v)  = the order-preserving integer image of a float (sign bit flipped for positive values, all bits for
+//             negative ones; -0 canonicalised to +0 first);
+//   x < 1/2:  cell = (key(x) - key(tab[0])) >> shiftA                       in [0, CELLS/2)
+//   x >= 1/2: cell = CELLS - 1 - ((key(1 - x) - key(1 - tab[K-1])) >> shiftB)  in [CELLS/2, CELLS)
+// Both halves are compositions of monotone maps (fl(1 - x) is monotone in x), so cell() is monotone on all floats.
+// The cells are log-spaced towards 0 AND towards 1, where base probabilities and therefore split thresholds crowd;
+// equal-width cells (first version, 3.8 ms) and cells log-spaced towards 0 only (second, 3.2 ms: 169 instructions per
+// warp and element, long divergent searches inside the few cells of [0.5, 1)) leave most thresholds in a few cells.
+// lut[c] = first threshold of cell c | number of thresholds in it << 16, built on the host with the same function.
 __host__ __device__ __forceinline__ uint32_t gbt_float_key(float x) {
     x = x + 0.0f;   // -0 -> +0 (exact); NaN never reaches here
 #ifdef __CUDA_ARCH__
@@ -65,23 +69,39 @@ __host__ __device__ __forceinline__ uint32_t gbt_float_key(float x) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__device__ __forceinline__ uint32_t gbt_rank_lut(const float* __restrict__ tab, const uint32_t* __restrict__ lut, int K, float tmin,
-                                                 float tmax, uint32_t kmin, int shift, float x) {
-    if (x != x) return 0xFFFFu;
-    if (K == 0 || x < tmin) return 0u;
-    if (x >= tmax) return (uint32_t)K;
-    const uint32_t e = lut[min((gbt_float_key(x) - kmin) >> shift, (uint32_t)(GBT_RANK_CELLS - 1))];
-    int lo = (int)(e & 0xffffu), n = (int)(e >> 16);
-    if (n <= 8) {
-        while (n > 0 && tab[lo] <= x) { lo++; n--; }
-        return (uint32_t)lo;
+__host__ __device__ __forceinline__ uint32_t gbt_rank_cell(const GbtRankCells& c, float x) {   // tmin <= x < tmax
+    constexpr uint32_t H = GBT_RANK_CELLS / 2;
+    if (x < 0.5f) {
+        const uint32_t d = gbt_float_key(x) - c.kminA;
+        const uint32_t q = d >> c.shiftA;
+        return q < H - 1 ? q : H - 1;
     }
-    int hi = lo + n;   // #{i : tab[i] <= x} within [lo, hi)
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (tab[mid] <= x) lo = mid + 1; else hi = mid;
+#ifdef __CUDA_ARCH__
+    const float u = __fsub_rn(1.0f, x);
+#else
+    const float u = 1.0f - x;
+#endif
+    const uint32_t d = gbt_float_key(u) - c.kminB;
+    const uint32_t q = d >> c.shiftB;
+    return GBT_RANK_CELLS - 1 - (q < H - 1 ? q : H - 1);
+}
+
+// tab = the sorted thresholds followed by GBT_RANK_PAD NaN sentinels (`NaN <= x` is false): the four entries from the
+// cell's first threshold on are compared without a branch -- thresholds of higher cells are > x, so reading past the
+// cell's own entries is harmless -- and only an x that passes all four keeps scanning (rare).  x outside
+// [tab[0], tab[K-1]) takes its cell from the clamped value and its comparisons from x itself: below the table nothing
+// is <= x (rank 0), above it everything is (the scan runs from the last cell's first entry to the sentinel: rank K).
+constexpr int GBT_RANK_PAD = 4;
+__device__ __forceinline__ uint32_t gbt_rank_lut(const float* __restrict__ tab, const uint32_t* __restrict__ lut,
+                                                 const GbtRankCells& c, float x) {
+    const float xs = fminf(fmaxf(x, c.tmin), c.tmax);   // NaN -> tmin (its rank is replaced below)
+    const uint32_t lo = lut[gbt_rank_cell(c, xs)] & 0xffffu;
+    const float* t = tab + lo;
+    uint32_t r = lo + (t[0] <= x) + (t[1] <= x) + (t[2] <= x) + (t[3] <= x);
+    if (t[3] <= x) {
+        while (tab[r] <= x) r++;
     }
-    return (uint32_t)lo;
+    return (x != x) ? 0xFFFFu : r;
 }
 
 // One CTA pass = one tile of 32 haplotypes x RANK_EL padded elements.  Reads are coalesced along a haplotype's row
@@ -90,44 +110,53 @@ __device__ __forceinline__ uint32_t gbt_rank_lut(const float* __restrict__ tab, 
 constexpr int RANK_EL = 256;
 constexpr int RANK_THREADS = 1024;
 constexpr int RANK_TS = 34;   // u16 per tile row (32 haplotypes + 2: rows 17 words apart, conflict-free transposition)
+template <bool TAB_SMEM>
 __global__ void __launch_bounds__(RANK_THREADS, 2)
-gbt_rank_tile_kernel(const float* __restrict__ thr, const uint32_t* __restrict__ lut_g, int K, float tmin, float tmax, uint32_t kmin, int shift,
-                     int table_in_smem, const float* __restrict__ B, int64_t N, int W, int A, int S, uint16_t* __restrict__ R2) {
+gbt_rank_tile_kernel(const float* __restrict__ thr, const uint32_t* __restrict__ lut_g, int K, GbtRankCells cells,
+                     const float* __restrict__ B, int64_t N, int W, int A, int S, uint16_t* __restrict__ R2) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t* tile = reinterpret_cast<uint16_t*>(smem);
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem + RANK_EL * RANK_TS * 2);
-    const float* tab = thr;
+    float* tab_s = reinterpret_cast<float*>(smem + RANK_EL * RANK_TS * 2 + GBT_RANK_CELLS * 4);
     for (int i = threadIdx.x; i < GBT_RANK_CELLS; i += blockDim.x) lut[i] = __ldg(lut_g + i);
-    if (table_in_smem) {
-        float* t = reinterpret_cast<float*>(smem + RANK_EL * RANK_TS * 2 + GBT_RANK_CELLS * 4);
-        for (int i = threadIdx.x; i < K; i += blockDim.x) t[i] = __ldg(thr + i);
-        tab = t;
-    }
+    if (TAB_SMEM)   // (the global copy carries the same sentinels)
+        for (int i = threadIdx.x; i < K + GBT_RANK_PAD; i += blockDim.x) tab_s[i] = __ldg(thr + i);
+    const float* tab = TAB_SMEM ? tab_s : thr;
     const int pad = (S + 1) / 2, Wp = W + S - 1, E = Wp * A;
+    const int e_lo = pad * A, e_hi = (pad + W) * A;            // padded elements [e_lo, e_hi) are B's own, in order
     const int runs = (E + RANK_EL - 1) / RANK_EL;
     const int64_t nhb = (N + 31) / 32, items = nhb * runs;
     const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;   // h = haplotype of the block this warp reads
+    const int dj = 32 / A, da = 32 - dj * A;                   // (slot, class) advance of 32 elements
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
         const int64_t hb = it / runs;
         const int e0 = (int)(it - hb * runs) * RANK_EL;
         const int64_t n = hb * 32 + h;
         const float* bn = B + n * (int64_t)W * A;
         float x[RANK_EL / 32];
+        if (e0 >= e_lo && e0 + RANK_EL <= e_hi) {              // interior tile: one contiguous run of the row
+            const float* src = bn + (e0 - e_lo) + lane;
 #pragma unroll
-        for (int q = 0; q < RANK_EL / 32; q++) {
-            const int e = e0 + q * 32 + lane;
-            x[q] = 0.f;
-            if (n < N && e < E) {
-                const int j = e / A, a = e - j * A;
-                x[q] = __ldg(bn + (int64_t)spad_to_orig(j, W, pad) * A + a);
+            for (int q = 0; q < RANK_EL / 32; q++) x[q] = (n < N) ? __ldg(src + q * 32) : 0.f;
+        } else {
+            int j = (e0 + lane) / A, a = (e0 + lane) - j * A;
+#pragma unroll
+            for (int q = 0; q < RANK_EL / 32; q++) {
+                const int e = e0 + q * 32 + lane;
+                x[q] = 0.f;
+                if (n < N && e < E) x[q] = __ldg(bn + spad_to_orig(j, W, pad) * A + a);
+                j += dj;
+                a += da;
+                if (a >= A) { a -= A; j++; }
             }
         }
         __syncthreads();   // the previous tile has left shared memory (and, first time round, lut / tab are in place)
 #pragma unroll
         for (int q = 0; q < RANK_EL / 32; q++) {
-            const int e = e0 + q * 32 + lane;
-            uint16_t r = 0;
-            if (n < N && e < E) r = (uint16_t)gbt_rank_lut(tab, lut, K, tmin, tmax, kmin, shift, x[q]);
+            // lanes beyond N / elements beyond E rank 0.f like any value: harmless, the first are never read back as
+            // data of a real haplotype and the second are not written below
+            uint16_t r = (uint16_t)gbt_rank_lut(tab, lut, cells, x[q]);
+            if (n >= N) r = 0;
             tile[(q * 32 + lane) * RANK_TS + h] = r;
         }
         __syncthreads();
@@ -145,32 +174,45 @@ gbt_rank_tile_kernel(const float* __restrict__ thr, const uint32_t* __restrict__
 }
 
 // model-create half of the rank pass: the cell table (see above).  Returns 0 / non-zero like the C ABI.
-int gbt_rank_lut_build(const float* tab_host, int K, float* tmin, float* tmax, uint32_t* kmin, int* shift, uint32_t** lut_dev) {
+int gbt_rank_lut_build(const float* tab_host, int K, GbtRankCells* cells, uint32_t** lut_dev, float** tab_dev) {
     std::vector<uint32_t> lut(GBT_RANK_CELLS, 0u);
-    *tmin = K ? tab_host[0] : 0.f;
-    *tmax = K ? tab_host[K - 1] : 0.f;
-    *kmin = K ? gbt_float_key(*tmin) : 0u;
-    *shift = 0;
+    GbtRankCells c{};
+    c.tmin = K ? tab_host[0] : 0.f;
+    c.tmax = K ? tab_host[K - 1] : 0.f;
     if (K > 0) {
-        const uint32_t span = gbt_float_key(*tmax) - *kmin;
-        while ((span >> *shift) >= (uint32_t)GBT_RANK_CELLS) (*shift)++;
+        constexpr uint32_t H = GBT_RANK_CELLS / 2;
+        for (int i = 0; i < K; i++)
+            GNX_REQUIRE(tab_host[i] == tab_host[i] && (i == 0 || tab_host[i] >= tab_host[i - 1]), "gnx_gbt_model_create: threshold table is not sorted");
+        // lower half: keys of [tab[0], 1/2); upper half: keys of 1 - x for x in [1/2, tab[K-1]], i.e. of [1 - tab[K-1], 1/2]
+        c.kminA = gbt_float_key(c.tmin);
+        const uint32_t khalf = gbt_float_key(0.5f);
+        const uint32_t spanA = khalf > c.kminA ? khalf - c.kminA : 0u;
+        while ((spanA >> c.shiftA) >= H) c.shiftA++;
+        c.kminB = gbt_float_key(1.0f - c.tmax);
+        const uint32_t spanB = khalf > c.kminB ? khalf - c.kminB : 0u;
+        while ((spanB >> c.shiftB) >= H) c.shiftB++;
         std::vector<uint32_t> cnt(GBT_RANK_CELLS, 0u);
         uint32_t prev = 0;
         for (int i = 0; i < K; i++) {
-            GNX_REQUIRE(tab_host[i] == tab_host[i] && (i == 0 || tab_host[i] >= tab_host[i - 1]), "gnx_gbt_model_create: threshold table is not sorted");
-            const uint32_t c = std::min<uint32_t>((gbt_float_key(tab_host[i]) - *kmin) >> *shift, GBT_RANK_CELLS - 1);
-            GNX_REQUIRE(c >= prev, "gnx_gbt_model_create: rank cells are not monotone");
-            prev = c;
-            cnt[c]++;
+            // the last threshold is never looked up (x >= tmax returns K first) but must keep the cells monotone
+            const uint32_t cell = gbt_rank_cell(c, tab_host[i]);
+            GNX_REQUIRE(cell < (uint32_t)GBT_RANK_CELLS && cell >= prev, "gnx_gbt_model_create: rank cells are not monotone");
+            prev = cell;
+            cnt[cell]++;
         }
         uint32_t start = 0;
-        for (int c = 0; c < GBT_RANK_CELLS; c++) {
-            lut[c] = start | (cnt[c] << 16);
-            start += cnt[c];
+        for (int k = 0; k < GBT_RANK_CELLS; k++) {
+            lut[k] = start | (cnt[k] << 16);
+            start += cnt[k];
         }
     }
+    *cells = c;
     GNX_CUDA(cudaMalloc((void**)lut_dev, GBT_RANK_CELLS * sizeof(uint32_t)));
     GNX_CUDA(cudaMemcpy(*lut_dev, lut.data(), GBT_RANK_CELLS * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    std::vector<float> padded(tab_host, tab_host + K);
+    padded.resize((size_t)K + GBT_RANK_PAD, nanf(""));
+    GNX_CUDA(cudaMalloc((void**)tab_dev, padded.size() * sizeof(float)));
+    GNX_CUDA(cudaMemcpy(*tab_dev, padded.data(), padded.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -360,13 +402,18 @@ int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, floa
     if (m->profile) GNX_CUDA(cudaEventRecord(m->ev[0], st));
     {
         const size_t fixed = (size_t)RANK_EL * RANK_TS * 2 + GBT_RANK_CELLS * 4;
-        const int in_smem = fixed + (size_t)m->d.K * 4 <= 110 * 1024;   // two CTAs per SM
-        const size_t rsm = fixed + (in_smem ? (size_t)m->d.K * 4 : 0);
-        GNX_CUDA(cudaFuncSetAttribute(gbt_rank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024)));
+        const size_t tab_bytes = (size_t)(m->d.K + GBT_RANK_PAD) * 4;
+        const int in_smem = fixed + tab_bytes <= 110 * 1024;   // two CTAs per SM
+        const size_t rsm = fixed + (in_smem ? tab_bytes : 0);
         const int64_t items = nhb * ceil_div((int64_t)Wp * A, RANK_EL);
         const int grid = (int)std::min<int64_t>(items, (int64_t)sm_count() * 2);
-        gbt_rank_tile_kernel<<<grid, RANK_THREADS, rsm, st>>>(m->d.thr_table, m->rank_lut, m->d.K, m->rank_tmin, m->rank_tmax, m->rank_kmin,
-                                                              m->rank_shift, in_smem, B_dev, N, W, A, S, R2);
+        if (in_smem) {
+            GNX_CUDA(cudaFuncSetAttribute(gbt_rank_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024)));
+            gbt_rank_tile_kernel<true><<<grid, RANK_THREADS, rsm, st>>>(m->rank_tab, m->rank_lut, m->d.K, m->rank_cells, B_dev, N, W, A, S, R2);
+        } else {
+            GNX_CUDA(cudaFuncSetAttribute(gbt_rank_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024)));
+            gbt_rank_tile_kernel<false><<<grid, RANK_THREADS, rsm, st>>>(m->rank_tab, m->rank_lut, m->d.K, m->rank_cells, B_dev, N, W, A, S, R2);
+        }
         GNX_CUDA(cudaGetLastError());
     }
     if (m->profile) GNX_CUDA(cudaEventRecord(m->ev[1], st));

@@ -170,6 +170,210 @@ svc_kernel_window(SvcDev m, SvcWin w, const uint32_t* __restrict__ QP, int64_t q
     }
 }
 
+// ------------------------------------------------------------------------------ K2, production form
+// The same sums for the reference's own Ms list -- lengths {1, 4, 8} below 33 (every CovSample(., 0.6, 1.0, 37) list
+// starts 1, 4, 8, 39, ...) -- for a GROUP of windows per launch (blockIdx.z), rebuilt around the two pipes the first
+// kernel saturates together (ncu, profiles/r2_ncu_svc_summary.txt: 43 instructions and 5 quarter-rate POPC / FLO per
+// word pair):
+//   * counts: popc(z) + popc(r4) + popc(r8) summed over the words of a window is a population count of 3 * nw words;
+//     they go through a carry-save adder tree (Harley-Seal: bit-sliced accumulators ones / twos / fours, 10 CSAs = 20
+//     LOP3 per 4 words) and only the two carries that leave a 4-word block are counted with POPC: 0.5 instead of 3
+//     quarter-rate instructions per word;
+//   * long runs: the open run is kept as its START position, so an all-match word costs nothing but the predicate;
+//     the run that closes in a word ends at its first mismatch, popc(z & (~z - 1)) SNPs in, and the next one starts
+//     after the last mismatch (FLO); its table g(L) = sum_{m in Ms, 32 < m <= L} (L - m + 1) sits in shared memory;
+//   * the word loop is unrolled by 4 with every shared-memory address a base register + immediate; the tail mask and
+//     one all-mismatch word behind the window (it closes a run that reaches the window's end) are folded into the
+//     operands once per word instead of once per pair.
+// Results are the same integers as svc_kernel_window<13> (GNX_SVC_KERNEL=0 selects that one; tests compare both).
+__device__ __forceinline__ void svc_csa(uint32_t& acc, uint32_t a, uint32_t b, uint32_t& carry) {
+    const uint32_t u = acc ^ a;
+    carry = (acc & a) | (u & b);
+    acc = u ^ b;
+}
+
+struct SvcPair {
+    uint32_t zp, r2p, r4p;        // previous word of the doubling chain
+    uint32_t ones, twos, fours;   // bit-sliced counters of the carry-save tree
+    uint32_t hold_in, hold_t, hold_f;
+    int start, k;
+};
+
+// one word of one (query, support vector) pair; phase = word index within the 4-word block (compile time)
+__device__ __forceinline__ int svc_lds_s32(uint32_t saddr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+template <int PHASE>
+__device__ __forceinline__ void svc_word(SvcPair& s, uint32_t nz, int base, int min_big, uint32_t gb) {
+    const uint32_t z = ~nz;
+    const uint32_t r2 = z & __funnelshift_l(s.zp, z, 1);
+    const uint32_t r4 = r2 & __funnelshift_l(s.r2p, r2, 2);
+    const uint32_t r8 = r4 & __funnelshift_l(s.r4p, r4, 4);
+    s.zp = z; s.r2p = r2; s.r4p = r4;
+    // run bookkeeping
+    const int t1 = __popc(z & (nz - 1u));                 // matches before the first mismatch (32 when there is none)
+    const int L = base + t1 - s.start;
+    const bool closed = nz != 0u;
+    // branch-free: entry 0 of the run table is 0 (gb = its shared address)
+    s.k += svc_lds_s32(gb + 4u * (uint32_t)((closed && L >= min_big) ? L : 0));
+    const int ns = base + 32 - __clz(nz);                 // position behind the last mismatch
+    s.start = closed ? ns : s.start;
+    // carry-save tree over the inputs z, r4, r8 of four consecutive words
+    uint32_t c;
+    if (PHASE == 0) {
+        svc_csa(s.ones, z, r4, s.hold_t);
+        s.hold_in = r8;
+    } else if (PHASE == 1) {
+        svc_csa(s.ones, s.hold_in, z, c);
+        uint32_t c2;
+        svc_csa(s.ones, r4, r8, c2);
+        uint32_t f1;
+        svc_csa(s.twos, s.hold_t, c, f1);
+        s.hold_t = c2;
+        s.hold_f = f1;
+    } else if (PHASE == 2) {
+        svc_csa(s.ones, z, r4, c);
+        uint32_t f2, e1;
+        svc_csa(s.twos, s.hold_t, c, f2);
+        svc_csa(s.fours, s.hold_f, f2, e1);
+        s.k += __popc(e1) << 3;
+        s.hold_in = r8;
+    } else {
+        svc_csa(s.ones, s.hold_in, z, c);
+        uint32_t c2, f3;
+        svc_csa(s.ones, r4, r8, c2);
+        svc_csa(s.twos, c, c2, f3);
+        s.k += __popc(f3) << 2;
+    }
+}
+
+// four words (one carry-save block) of the SB x 2 pairs a warp holds; MASKED blocks apply the window's tail mask /
+// the all-mismatch words behind the window, interior blocks need neither
+template <int SB, bool MASKED>
+__device__ __forceinline__ void svc_block(SvcPair (&st)[2][SB], const uint32_t* __restrict__ pa0, const uint32_t* __restrict__ pa1,
+                                          const uint32_t* __restrict__ pb0, const uint32_t* __restrict__ pb1,
+                                          const uint32_t* const (&py)[SB][2], int j0, int nw, uint32_t tail, int min_big,
+                                          uint32_t gb) {
+#pragma unroll
+    for (int ph = 0; ph < 4; ph++) {
+        const int j = j0 + ph;
+        uint32_t keep = 0xffffffffu;
+        if (MASKED) keep = (j < nw - 1) ? 0xffffffffu : ((j == nw - 1) ? tail : 0u);
+        uint32_t x0[2], x1[2];
+        x0[0] = pa0[ph]; x1[0] = pa1[ph];
+        x0[1] = pb0[ph]; x1[1] = pb1[ph];
+        if (MASKED) { x1[0] |= ~keep; x1[1] |= ~keep; }
+#pragma unroll
+        for (int b = 0; b < SB; b++) {
+            const uint32_t y0 = py[b][0][ph];
+            uint32_t y1 = py[b][1][ph];
+            if (MASKED) y1 &= keep;
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const uint32_t nz = (x0[a] ^ y0) | (x1[a] ^ y1);
+                if (ph == 0) svc_word<0>(st[a][b], nz, j * 32, min_big, gb);
+                else if (ph == 1) svc_word<1>(st[a][b], nz, j * 32, min_big, gb);
+                else if (ph == 2) svc_word<2>(st[a][b], nz, j * 32, min_big, gb);
+                else svc_word<3>(st[a][b], nz, j * 32, min_big, gb);
+            }
+        }
+    }
+}
+
+constexpr int SVC_SB = 2;   // support vectors a warp walks at once (x 2 queries per lane)
+
+__global__ void __launch_bounds__(SVC_THREADS, 3)
+svc_kernel_csa(SvcDev m, const SvcWin* __restrict__ wins, int w0, const uint32_t* __restrict__ QP, int64_t qp_words, int64_t N,
+               int32_t* __restrict__ Kt, int64_t ldK, int64_t kt_win_stride, int32_t* __restrict__ Krow) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    const SvcWin w = wins[w0 + blockIdx.z];
+    const int s0 = blockIdx.y * SVC_CHUNK;
+    if (s0 >= w.nsv) return;
+    const int nw = w.nw;
+    const int nblk = (nw + 1 + 3) / 4;   // the window's words plus at least one all-mismatch word behind it
+    const int rs = (4 * nblk) | 1;       // row stride in words: whole blocks are addressable, odd for the banks
+    uint32_t* qp = sm;                               // [64][2][rs]
+    uint32_t* sp = qp + (size_t)SVC_Q * 2 * rs;      // [SVC_CHUNK][2][rs]
+    int32_t* gb = reinterpret_cast<int32_t*>(sp + (size_t)SVC_CHUNK * 2 * rs);   // [len + 1]
+    const uint32_t gb_s = (uint32_t)__cvta_generic_to_shared(gb);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n0 = (int64_t)blockIdx.x * SVC_Q;
+    if (Kt) Kt += (int64_t)blockIdx.z * kt_win_stride;
+    const int ns = min(SVC_CHUNK, w.nsv - s0);
+    {
+        const int64_t wi0 = w.lo >> 5;
+        const int sh = (int)(w.lo & 31);
+        for (int i = threadIdx.x; i < SVC_Q * 2 * rs; i += SVC_THREADS) {
+            const int row = i / rs, j = i - row * rs;
+            const int64_t n = n0 + (row >> 1);
+            uint32_t v = 0u;
+            if (n < N && j < nw) {
+                const uint32_t* src = QP + ((size_t)n * 2 + (row & 1)) * qp_words + wi0 + j;
+                v = __funnelshift_r(__ldg(src), __ldg(src + 1), sh);
+            }
+            qp[i] = v;
+        }
+        const uint32_t* src = w.planes + (size_t)s0 * 2 * nw;
+        for (int i = threadIdx.x; i < SVC_CHUNK * 2 * rs; i += SVC_THREADS) {
+            const int row = i / rs, j = i - row * rs;
+            sp[i] = (row < ns * 2 && j < nw) ? __ldg(src + (size_t)row * nw + j) : 0u;
+        }
+        for (int i = threadIdx.x; i <= w.len; i += SVC_THREADS) gb[i] = __ldg(m.gbig + i);
+    }
+    __syncthreads();
+    const uint32_t tail = (w.len & 31) ? ((1u << (w.len & 31)) - 1u) : 0xffffffffu;
+    const int min_big = m.min_big;
+    const int nfull = (nw - 1) / 4;      // blocks whose four words all lie before the window's last word
+    constexpr int SB = SVC_SB;
+    for (int sb = warp * (SVC_CHUNK / 8); sb < (warp + 1) * (SVC_CHUNK / 8) && sb < ns; sb += SB) {
+        SvcPair st[2][SB];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < SB; b++) st[a][b] = SvcPair{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0, 0};
+        const uint32_t* pa0 = qp + (size_t)(lane * 2) * rs;
+        const uint32_t* pa1 = pa0 + rs;
+        const uint32_t* pb0 = qp + (size_t)((lane + 32) * 2) * rs;
+        const uint32_t* pb1 = pb0 + rs;
+        const uint32_t* py[SB][2];
+#pragma unroll
+        for (int b = 0; b < SB; b++) {
+            py[b][0] = sp + (size_t)((sb + b) * 2) * rs;   // rows behind the chunk's last vector are zero
+            py[b][1] = py[b][0] + rs;
+        }
+        int blk = 0;
+#pragma unroll 1
+        for (; blk < nfull; blk++) {
+            svc_block<SB, false>(st, pa0, pa1, pb0, pb1, py, blk * 4, nw, tail, min_big, gb_s);
+            pa0 += 4; pa1 += 4; pb0 += 4; pb1 += 4;
+#pragma unroll
+            for (int b = 0; b < SB; b++) { py[b][0] += 4; py[b][1] += 4; }
+        }
+#pragma unroll 1
+        for (; blk < nblk; blk++) {
+            svc_block<SB, true>(st, pa0, pa1, pb0, pb1, py, blk * 4, nw, tail, min_big, gb_s);
+            pa0 += 4; pa1 += 4; pb0 += 4; pb1 += 4;
+#pragma unroll
+            for (int b = 0; b < SB; b++) { py[b][0] += 4; py[b][1] += 4; }
+        }
+#pragma unroll
+        for (int b = 0; b < SB; b++)
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const SvcPair& s = st[a][b];
+                const int k = s.k + __popc(s.ones) + 2 * __popc(s.twos) + 4 * __popc(s.fours);
+                const int64_t n = n0 + lane + 32 * a;
+                if (n < N && sb + b < ns) {
+                    if (Kt) Kt[(int64_t)(s0 + sb + b) * ldK + n] = k;
+                    else Krow[n * w.nsv + s0 + sb + b] = k;
+                }
+            }
+    }
+}
+
 // Bit planes of the reflect-padded haplotypes (src/Base/base.py:41-44), once per predict call:
 // QP[n][plane][word], bit b of word j = plane bit of padded column 32 j + b; one spare zero word.
 __global__ void svc_pack_kernel(SvcDev m, const int8_t* __restrict__ X, int64_t N, int64_t ldX, uint32_t* __restrict__ QP,
@@ -261,8 +465,12 @@ __device__ void svc_multiclass_probability(int k, const double* r, double* p) {
 // K3a: thread = one (haplotype, class pair): the pairwise decision value in libsvm's order (class i's
 // support vectors, then class j's), Platt sigmoid -> r_ij into R[p][n]
 __global__ void __launch_bounds__(128)
-svc_pair_window(SvcDev m, SvcWin w, const int32_t* __restrict__ Kt, int64_t ldK, int64_t N, double* __restrict__ R) {
+svc_pair_window(SvcDev m, const SvcWin* __restrict__ wins, int w0, const int32_t* __restrict__ Kt, int64_t ldK, int64_t kt_win_stride,
+                int64_t N, double* __restrict__ R) {
     __shared__ int s_start[SVC_MAX_A + 1];
+    const SvcWin w = wins[w0 + blockIdx.z];
+    Kt += (int64_t)blockIdx.z * kt_win_stride;
+    R += (int64_t)blockIdx.z * m.P * ldK;
     if (threadIdx.x == 0) {
         s_start[0] = 0;
         for (int c = 0; c < m.A; c++) s_start[c + 1] = s_start[c] + w.n_support[c];
@@ -294,9 +502,11 @@ svc_pair_window(SvcDev m, SvcWin w, const int32_t* __restrict__ Kt, int64_t ldK,
 
 // K3b: thread = one haplotype: pairwise coupling of the P pair probabilities
 __global__ void __launch_bounds__(128)
-svc_couple_window(SvcDev m, int wi, const double* __restrict__ R, int64_t ldK, int64_t N, double* __restrict__ B) {
+svc_couple_window(SvcDev m, int w0, const double* __restrict__ R, int64_t ldK, int64_t N, double* __restrict__ B) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    const int wi = w0 + blockIdx.y;
+    R += (int64_t)blockIdx.y * m.P * ldK;
     const int k = m.A;
     double pair[SVC_MAX_A * SVC_MAX_A];
     int p = 0;
@@ -323,6 +533,8 @@ svc_couple_window(SvcDev m, int wi, const double* __restrict__ R, int64_t ldK, i
 struct gnx_svc {
     gnx::SvcDev d;
     std::vector<gnx::SvcWin> win;
+    gnx::SvcWin* d_win;   // the same descriptors on the device (window groups index them by blockIdx.z)
+    int use_csa;          // 1: svc_kernel_csa for the reference's Ms list (GNX_SVC_KERNEL=0: first kernel)
     int device;
     int max_nsv;
     void* d_blob;
@@ -446,6 +658,19 @@ int gnx_svc_model_create(gnx_svc_t** out, int A, int64_t C, int64_t M, int64_t c
         sw.probA = reinterpret_cast<const double*>(blob + o_pa) + w * P;
         sw.probB = reinterpret_cast<const double*>(blob + o_pb) + w * P;
     }
+    m->d_win = nullptr;
+    if (cudaMalloc((void**)&m->d_win, sizeof(SvcWin) * (size_t)W) != cudaSuccess ||
+        cudaMemcpy(m->d_win, m->win.data(), sizeof(SvcWin) * (size_t)W, cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (m->d_win) cudaFree(m->d_win);
+        cudaFree(blob);
+        delete m;
+        set_error("gnx_svc_model_create: window table copy failed");
+        return 1;
+    }
+    {
+        const char* e2 = getenv("GNX_SVC_KERNEL");
+        m->use_csa = !(e2 && e2[0] == '0');
+    }
     cudaGetDevice(&m->device);
     m->d_blob = blob;
     m->max_nsv = max_nsv;
@@ -458,6 +683,7 @@ int gnx_svc_model_create(gnx_svc_t** out, int A, int64_t C, int64_t M, int64_t c
 void gnx_svc_model_destroy(gnx_svc_t* m) {
     if (!m) return;
     if (m->d_blob) cudaFree(m->d_blob);
+    if (m->d_win) cudaFree(m->d_win);
     delete m;
 }
 
@@ -471,10 +697,33 @@ static int svc_pack(const gnx_svc_t* m, const int8_t* X, int64_t N, int64_t ldX,
     return 0;
 }
 
+static bool svc_uses_csa(const gnx_svc_t* m) { return m->d.fast && m->d.small_mask == 13 && m->use_csa; }
+
+// windows [w0, w0 + g) in one launch of the production kernel
+static int svc_launch_csa(const gnx_svc_t* m, int w0, int g, const uint32_t* QP, int64_t N, int32_t* Kt, int64_t ldK, int64_t kt_win,
+                          int32_t* Krow, cudaStream_t st) {
+    int nsv_max = 0, nw_max = 0, len_max = 0;
+    for (int w = w0; w < w0 + g; w++) {
+        nsv_max = std::max(nsv_max, m->win[w].nsv);
+        nw_max = std::max(nw_max, m->win[w].nw);
+        len_max = std::max(len_max, m->win[w].len);
+    }
+    if (nsv_max == 0) return 0;
+    const size_t rs_max = (size_t)((4 * ((nw_max + 1 + 3) / 4)) | 1);
+    const size_t smem = ((size_t)SVC_Q * 2 * rs_max + (size_t)SVC_CHUNK * 2 * rs_max + (size_t)len_max + 2) * 4;
+    GNX_REQUIRE(smem <= 227 * 1024, "gnx_svc: window of %d SNPs too long for shared memory", len_max);
+    GNX_CUDA(cudaFuncSetAttribute(svc_kernel_csa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ceil_div(N, SVC_Q), (unsigned)ceil_div(nsv_max, SVC_CHUNK), (unsigned)g);
+    svc_kernel_csa<<<grid, SVC_THREADS, smem, st>>>(m->d, m->d_win, w0, QP, svc_qp_words(m), N, Kt, ldK, kt_win, Krow);
+    GNX_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int svc_launch_kernel(const gnx_svc_t* m, int w, const int8_t* X, const uint32_t* QP, int64_t N, int64_t ldX, int32_t* Kt, int64_t ldK,
                              int32_t* Krow, cudaStream_t st) {
     const SvcWin& sw = m->win[w];
     if (sw.nsv == 0) return 0;
+    if (svc_uses_csa(m)) return svc_launch_csa(m, w, 1, QP, N, Kt, ldK, 0, Krow, st);
     if (m->d.fast) {
         const size_t smem = ((size_t)SVC_Q * 2 * sw.nwp + (size_t)SVC_CHUNK * 2 * sw.nw) * 4;
         GNX_REQUIRE(smem <= 227 * 1024, "gnx_svc: window of %d SNPs too long for shared memory", sw.len);
@@ -518,8 +767,14 @@ int gnx_svc_predict(const gnx_svc_t* m, const int8_t* X_dev, int64_t N, int64_t 
     GNX_REQUIRE(X_dev && B_dev, "gnx_svc_predict: NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t ldK = (N + 31) & ~int64_t(31);
-    const size_t kt_bytes = (sizeof(int32_t) * (size_t)std::max(1, m->max_nsv) * ldK + 255) & ~size_t(255);
-    const size_t r_bytes = (sizeof(double) * (size_t)m->d.P * ldK + 255) & ~size_t(255);
+    const int W = m->d.W;
+    const bool csa = svc_uses_csa(m);
+    // windows per launch: enough CTAs to make the tail wave irrelevant, bounded by ~1 GB of kernel-value scratch
+    const int64_t kt_win = (int64_t)std::max(1, m->max_nsv) * ldK;   // int32 elements per window
+    int G = 1;
+    if (csa) G = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, W), (int64_t(1) << 28) / kt_win));
+    const size_t kt_bytes = (sizeof(int32_t) * (size_t)kt_win * G + 255) & ~size_t(255);
+    const size_t r_bytes = (sizeof(double) * (size_t)m->d.P * ldK * G + 255) & ~size_t(255);
     const size_t qp_bytes = m->d.fast ? sizeof(uint32_t) * (size_t)N * 2 * svc_qp_words(m) : 0;
     char* scratch = nullptr;
     GNX_CUDA(cudaMallocAsync((void**)&scratch, kt_bytes + r_bytes + qp_bytes + 256, st));
@@ -528,14 +783,21 @@ int gnx_svc_predict(const gnx_svc_t* m, const int8_t* X_dev, int64_t N, int64_t 
     uint32_t* QP = m->d.fast ? reinterpret_cast<uint32_t*>(scratch + kt_bytes + r_bytes) : nullptr;
     int rc = 0;
     if (QP) rc = svc_pack(m, X_dev, N, ldX, QP, st);
-    for (int w = 0; w < m->d.W && rc == 0; w++) {
-        rc = svc_launch_kernel(m, w, X_dev, QP, N, ldX, Kt, ldK, nullptr, st);
-        if (rc) break;
-        dim3 gp((unsigned)ceil_div(N, 128), (unsigned)m->d.P);
-        svc_pair_window<<<gp, 128, 0, st>>>(m->d, m->win[w], Kt, ldK, N, R);
-        svc_couple_window<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(m->d, w, R, ldK, N, B_dev);
+    for (int w0 = 0; w0 < W && rc == 0; w0 += G) {
+        const int g = std::min(G, W - w0);
+        if (csa) {
+            rc = svc_launch_csa(m, w0, g, QP, N, Kt, ldK, kt_win, nullptr, st);
+            if (rc) break;
+        } else {
+            rc = svc_launch_kernel(m, w0, X_dev, QP, N, ldX, Kt, ldK, nullptr, st);
+            if (rc) break;
+        }
+        dim3 gp((unsigned)ceil_div(N, 128), (unsigned)m->d.P, (unsigned)g);
+        svc_pair_window<<<gp, 128, 0, st>>>(m->d, m->d_win, w0, Kt, ldK, kt_win, N, R);
+        dim3 gc((unsigned)ceil_div(N, 128), (unsigned)g);
+        svc_couple_window<<<gc, 128, 0, st>>>(m->d, w0, R, ldK, N, B_dev);
         if (cudaGetLastError() != cudaSuccess) {
-            set_error("gnx_svc_predict: launch failed (window %d)", w);
+            set_error("gnx_svc_predict: launch failed (window %d)", w0);
             rc = 1;
         }
     }

@@ -115,3 +115,52 @@ def test_covrsk_train_then_predict_roundtrip():
             Kfull = np.zeros((len(Xq), len(Xt)))
             Kfull[:, base.models[w].support_] = Kq
             assert np.max(np.abs(base.models[w].predict_proba(Kfull) - B[:, w, :])) < 1e-12
+
+
+@pytest.mark.parametrize("C,M,ctx,nsv,N,seed", [(4096, 512, 0, 50, 130, 5), (3000, 217, 108, 97, 64, 6), (1857, 857, 428, 49, 33, 7)])
+def test_production_kernel_equals_first_kernel_and_oracle(C, M, ctx, nsv, N, seed, monkeypatch):
+    """svc_kernel_csa (carry-save counts, start-position run bookkeeping, window groups) against svc_kernel_window<13>
+    and the oracle: window lengths that are / are not multiples of 32 and of 128, support-vector counts around the
+    48-vector chunk, a partial last block of 64 queries, runs crossing the whole window; the probabilities of
+    gnx_svc_predict (window groups) bit for bit between the two kernels."""
+    from oracle import c_oracle as co, np_oracle as npo
+    rng = np.random.default_rng(seed)
+    A = 3
+    founders = rng.integers(0, 2, size=(5, C)).astype(np.int8)
+
+    def mosaic(n):
+        out = founders[rng.integers(0, 5, n)].copy()
+        for i in range(n):
+            for c in np.sort(rng.integers(1, C, 2)):
+                out[i, c:] = founders[rng.integers(0, 5)][c:]
+        out[rng.random(out.shape) < 0.001] ^= 1
+        out[rng.random(out.shape) < 0.0005] = 2
+        return out
+    T, Xq = mosaic(nsv), mosaic(N)
+    Xq[0] = T[0]                                          # one query identical to a support vector: a run over every window
+    P = A * (A - 1) // 2
+
+    def build():
+        b = _base(C, M, A, ctx)
+        Tp = npo.base_pad(T, ctx) if ctx else T
+        sl = b.window_slices()
+        W = len(sl)
+        ns = np.array([nsv - 2 * (nsv // 3), nsv // 3, nsv // 3], np.int32)
+        r2 = np.random.default_rng(seed + 100)
+        b.set_window_svcs([Tp[:, lo:hi] for lo, hi in sl], [ns] * W, [r2.normal(0, 1e-3, (A - 1, nsv)) for _ in range(W)],
+                          [r2.normal(0, 0.1, P) for _ in range(W)], [np.full(P, -1.0)] * W, [np.zeros(P)] * W)
+        return b, sl, Tp
+    b_new, sl, Tp = build()
+    K_new = [b_new.kernel_window(w, Xq).cpu().numpy() for w in range(len(sl))]
+    B_new = b_new.predict_proba(Xq)
+    monkeypatch.setenv("GNX_SVC_KERNEL", "0")
+    b_old, _, _ = build()
+    K_old = [b_old.kernel_window(w, Xq).cpu().numpy() for w in range(len(sl))]
+    B_old = b_old.predict_proba(Xq)
+    monkeypatch.delenv("GNX_SVC_KERNEL")
+    Xp = npo.base_pad(Xq, ctx) if ctx else Xq
+    for w, (lo, hi) in enumerate(sl):
+        assert np.array_equal(K_new[w], K_old[w]), "window %d" % w
+        if w in (0, len(sl) - 1):
+            assert np.array_equal(K_new[w], co.covrsk(Xp[:, lo:hi], Tp[:, lo:hi], npo.cov_sample(hi - lo))), "window %d" % w
+    assert np.array_equal(B_new.view(np.uint64), B_old.view(np.uint64))
