@@ -68,3 +68,35 @@ def test_lr_empty_and_bad_shape():
     assert tuple(out.shape) == (0, C // M, A)
     with pytest.raises(AssertionError):
         base.predict_proba(torch.zeros((4, C - 1), dtype=torch.int8, device="cuda"))
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("name", ["base_lr_a3.npz", "base_lr_a7.npz", "base_lr_a2.npz"])
+def test_lr_against_reference_golden(name, kernel):
+    """K1 straight against the reference: real scikit-learn liblinear models trained through the reference's
+    Base.train and predicted through its Base.predict_proba (tests/golden/base_lr_a*.npz, oracle/make_golden.py):
+    float64 output within 1e-12, float32 output == the reference's float64 rounded to float32 except where the
+    reference value sits within 1e-12 of a float32 rounding boundary, labels (argmax) identical."""
+    import os
+    import torch
+    from tests.test_oracle_golden import _load, _split_coefs
+    d = _load(name)
+    C, M, A, ctx, coefs, icpts = _split_coefs(d)
+    X, B_ref = d["X"], d["B"]
+    base = util.make_lr_base(C, M, A, coefs, icpts, ctx_ratio=ctx / M)
+    assert base.context == ctx
+    base.kernel = kernel
+    Xd = torch.from_numpy(X).cuda()
+    Bd = base.predict_proba_f64(Xd).cpu().numpy()
+    assert Bd.shape == B_ref.shape and np.max(np.abs(Bd - B_ref)) < 1e-12
+    Bf = base.predict_proba(Xd).cpu().numpy()
+    ref32 = B_ref.astype(np.float32)
+    differ = Bf.view(np.uint32) != ref32.view(np.uint32)
+    # a float32 result may differ from round(reference float64) only by one ulp and only where the two float64
+    # values straddle a rounding boundary, i.e. where they differ at all (<= 1e-12)
+    assert differ.mean() < 1e-4
+    assert np.all(np.abs(Bf[differ].astype(np.float64) - B_ref[differ]) <= np.spacing(ref32[differ]).astype(np.float64))
+    assert np.array_equal(np.argmax(Bf, -1), np.argmax(B_ref, -1)) and np.array_equal(np.argmax(Bd, -1), np.argmax(B_ref, -1))
+    # the numpy-in / numpy-out plugin call returns the reference's dtype and values
+    B_np = base.predict_proba(X)
+    assert B_np.dtype == np.float64 and np.max(np.abs(B_np - B_ref)) < 1e-12
