@@ -295,12 +295,10 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->use_rank = 1;
     m->h_topc = nullptr;
     m->h_tiletop = nullptr;
-    m->h_tiletop3 = nullptr;
     m->rank_lut = nullptr;
     m->rank_tab = nullptr;
     m->profile = 0;
     m->ev[0] = m->ev[1] = m->ev[2] = nullptr;
-    m->tile_top_words = 4;
     m->tile_forest = nullptr;
     m->tile_forest_bytes = 0;
     m->block_forest = nullptr;
@@ -345,18 +343,14 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
                 memcpy(timg.data() + (size_t)t * 32 + 16, rimg.data() + (size_t)n_trees * RK_LOWER + (size_t)t * RK_LEAVES, sizeof(uint32_t) * RK_LEAVES);
             }
             m->h_tiletop = new GbtTileTop();
-            m->h_tiletop3 = new GbtTopC();
             for (int t = 0; t < n_trees; t++) {
                 const uint32_t t0 = conv(top[(size_t)t * 4]);
                 m->h_tiletop->q[t] = make_uint4(t0, conv(top[(size_t)t * 4 + 1]), conv(top[(size_t)t * 4 + 2]), t0 & 0x1ff80u);
-                for (int k = 0; k < 3; k++) m->h_tiletop3->w[3 * t + k] = conv(top[(size_t)t * 4 + k]);
             }
             if (gbt_rank_lut_build(tab.data(), K, &m->rank_cells, &m->rank_lut, &m->rank_tab)) {
                 gnx_gbt_model_destroy(m);
                 return 1;
             }
-            const char* tw = getenv("GNX_GBT_TOPW");
-            m->tile_top_words = (tw && atoi(tw) == 3) ? 3 : 4;
             void* d_t = nullptr;
             if (cudaMalloc(&d_t, timg.size() * 4) != cudaSuccess) return fail("tile image allocation failed");
             m->tile_forest = static_cast<const unsigned char*>(d_t);
@@ -383,7 +377,6 @@ void gnx_gbt_model_destroy(gnx_gbt_t* m) {
     for (int i = 0; i < 3; i++)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m->h_tiletop;
-    delete m->h_tiletop3;
     delete m->h_topc;
     delete m;
 }

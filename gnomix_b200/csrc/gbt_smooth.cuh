@@ -255,8 +255,6 @@ struct gnx_gbt {
     // tile kernel (gbt_tile.cu): node word = (k << 17) | (feature << 7); per tree one 128-byte record
     // { block u32 [16], leaves f32 [16] }; tree tops in the parameter bank
     gnx::GbtTileTop* h_tiletop;   // 4 words per tree
-    gnx::GbtTopC* h_tiletop3;     // 3 words per tree (GNX_GBT_TOPW=3)
-    int tile_top_words;
     uint32_t* rank_lut;           // [GBT_RANK_CELLS] first threshold of the cell | thresholds in it << 16
     gnx::GbtRankCells rank_cells; // monotone cell function of the rank pass (gbt_tile.cu)
     float* rank_tab;              // the threshold table followed by NaN sentinels

@@ -244,12 +244,6 @@ template <typename TOPT> struct TileTopLoad;
 template <> struct TileTopLoad<GbtTileTop> {   // one 16-byte uniform load: nodes 0, 1, 2 and node 0's feature offset
     static __device__ __forceinline__ uint4 get(const GbtTileTop& t, int i) { return t.q[i]; }
 };
-template <> struct TileTopLoad<GbtTopC> {      // three words per tree (smaller constant-cache footprint)
-    static __device__ __forceinline__ uint4 get(const GbtTopC& t, int i) {
-        const uint32_t t0 = t.w[3 * i];
-        return make_uint4(t0, t.w[3 * i + 1], t.w[3 * i + 2], t0 & TILE_FMASK);
-    }
-};
 
 template <int AT, typename TOPT>
 __global__ void __launch_bounds__(RK_THREADS, 1)
@@ -425,14 +419,7 @@ int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, floa
         gbt_smooth_tile_kernel<AT, TOPT><<<grid, RK_THREADS, smem, st>>>(TOPV, m->d, m->tile_forest, m->tile_forest_bytes, (uint32_t)tile_bytes, \
                                                                          R2, B_dev, N, W, nseg, Lseg, proba_dev, label_dev);  \
     } while (0)
-#define CALLT(AT)                                                  \
-    do {                                                           \
-        if (m->tile_top_words == 4) {                              \
-            LAUNCHT(AT, GbtTileTop, *m->h_tiletop);                \
-        } else {                                                   \
-            LAUNCHT(AT, GbtTopC, *m->h_tiletop3);                  \
-        }                                                          \
-    } while (0)
+#define CALLT(AT) LAUNCHT(AT, GbtTileTop, *m->h_tiletop)
     switch (A) {
         case 2: CALLT(2); break;
         case 3: CALLT(3); break;
