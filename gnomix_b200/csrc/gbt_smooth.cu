@@ -308,12 +308,14 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
         gnx_gbt_model_destroy(m);
         return 1;
     };
-    if (rank_ok && n_trees <= GBT_TOPC_MAX_T) {
+    if (rank_ok) {
         const uint32_t* lower = rimg.data();
         const uint32_t* top = rimg.data() + (size_t)n_trees * (RK_LOWER + RK_LEAVES);
-        m->h_topc = new GbtTopC();
-        for (int t = 0; t < n_trees; t++)
-            for (int k = 0; k < 3; k++) m->h_topc->w[3 * t + k] = top[(size_t)t * 4 + k];
+        if (n_trees <= GBT_TOPC_MAX_T) {   // tops for the parameter bank of the row kernel
+            m->h_topc = new GbtTopC();
+            for (int t = 0; t < n_trees; t++)
+                for (int k = 0; k < 3; k++) m->h_topc->w[3 * t + k] = top[(size_t)t * 4 + k];
+        }
         // block image (accumulating-offset walk of the row kernel): per tree 16 words -- level-2 node i2 at word
         // 4 * i2, level-3 node i3 at word 2 * i3 + 1 -- then the leaves of all trees
         std::vector<uint32_t> bimg((size_t)n_trees * (RK_BLOCK + RK_LEAVES), 0u);
@@ -361,7 +363,7 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
     m->variant = -1;  // chosen per call: tile kernel for batches of haplotypes, row kernel otherwise
     if (const char* e = getenv("GNX_GBT_VARIANT")) {  // profiling / cross-check switch
         const int v = atoi(e);
-        if (v == 0 || (v == 4 && m->block_forest) || (v == 6 && m->tile_forest)) m->variant = v;
+        if (v == 0 || (v == 4 && m->block_forest && m->h_topc) || (v == 6 && m->tile_forest)) m->variant = v;
     }
     *out = m;
     return 0;
@@ -415,7 +417,7 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
         // per haplotype when the chromosome fits shared memory; (G, Lseg) chosen for the best fit of
         // rows to the 1024 threads.
         const size_t slot_bytes = (size_t)m->d.astride * 4;
-        const int var = (m->variant == 0 || !m->block_forest) ? 0 : 4;
+        const int var = (m->variant == 0 || !m->block_forest || !m->h_topc) ? 0 : 4;
         const size_t img_bytes = (var == 4) ? m->block_forest_bytes : m->rank_forest_bytes;
         const unsigned char* img = (var == 4) ? m->block_forest : m->rank_forest;
         const size_t room = smem_max - img_bytes - 16;
@@ -486,7 +488,7 @@ int gnx_gbt_set_kernel(gnx_gbt_t* m, int which) {
     if (which == 0) m->variant = -1;
     if (which >= 10 && m->d.rank_ok) {  // not a rank-form forest: the generic kernel runs whatever is asked
         const int v = which - 10;
-        GNX_REQUIRE(v == 0 || (v == 4 && m->block_forest) || (v == 6 && m->tile_forest), "gnx_gbt_set_kernel: kernel %d not available for this forest", which);
+        GNX_REQUIRE(v == 0 || (v == 4 && m->block_forest && m->h_topc) || (v == 6 && m->tile_forest), "gnx_gbt_set_kernel: kernel %d not available for this forest", which);
         m->variant = v;
     }
     return 0;

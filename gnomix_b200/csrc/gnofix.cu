@@ -37,8 +37,13 @@
 //     unchanged when the whole scope sits in a swapped tail, the two candidates just trade places),
 //     and a rejected check changes no state, so skipping its repeats in later iterations is exact.
 //     Most of the reference's up-to-50 iterations re-run the same rejected checks.
-//   * A team of 256 threads owns one individual; three teams share one CTA and one copy of
+//   * A team of 256 threads owns one individual; up to four teams share one CTA and one copy of
 //     the forest in shared memory; teams pull individuals from a global counter.
+//   * The tree walk is the accumulating-offset walk of the row kernel (gbt_smooth.cuh: one byte offset
+//     addresses level-2 node, level-3 node and leaf inside a tree's block), with the three top nodes of a
+//     tree read from shared memory as one 16-byte load.  The tracker history (one row of window bits per
+//     outer iteration, read once per iteration) lives in global memory, which is what makes room for the
+//     fourth team.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -54,14 +59,17 @@ struct GfArgs {
     const uint16_t* ranks;   // [2n][W][A] rank of the ORIGINAL base probabilities
     const uint32_t* diff;    // [n][nw] bit j: original haplotypes differ in SNP block j
     uint32_t* trk_out;       // [n][nw] final tracker bits
+    uint32_t* hist;          // [grid * teams][max_it][nw] tracker history of the individual a team is working on
     int32_t* Y;              // [2n][W] in: smoother labels of the original pair; out: final labels
     int32_t* tracker;        // [2n][W] or NULL
     int* counter;            // work queue
     int64_t n_ind;
     int W, nw, max_it, teams;
     size_t team_bytes;
+    int leaf_words;          // floats of a team's leaf / margin buffer
     unsigned long long* stats;  // [4] iterations, scans, checks, accepted switches (summed over individuals)
     int memo;                // remember rejected checks (exact; GNX_GNOFIX_MEMO=0 re-runs them, for cross-checks)
+    int split;               // re-smoothing by (row, class) tasks (GNX_GNOFIX_SPLIT=0: one thread per row, for cross-checks)
 };
 
 __device__ __forceinline__ void team_sync(int team) {
@@ -70,21 +78,86 @@ __device__ __forceinline__ void team_sync(int team) {
 
 static unsigned long long* g_gnofix_stats = nullptr;
 
+constexpr int GF_MAX_TEAMS = 4;
+constexpr int GF_CH = 5;        // (row, class) chains a thread of the re-smoothing walks at once
+constexpr int GF_REC = 144;     // bytes of a tree in shared memory: block u32 [16] | leaves f32 [16] | top uint4
+
+__device__ __forceinline__ uint32_t gf_ld32(const unsigned char* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+// One tree for one row: the accumulating-offset walk of the row kernel (gbt_smooth.cuh: a single byte offset
+// o = 32 b0 + 16 b1 + 8 b2 + 4 b3 addresses level-2 node, level-3 node and leaf inside the tree's record) with the three top
+// nodes read from the record as one 16-byte load.  (The row kernel takes the tops from the parameter bank, free there because
+// all warps of its CTA are on the same tree; the teams of this kernel are not, the indexed constant loads queue up: measured
+// 17 % slower than shared-memory tops.)
+__device__ __forceinline__ float gf_tree(const unsigned char* __restrict__ row, const unsigned char* __restrict__ rec) {
+    const uint4 t4 = *reinterpret_cast<const uint4*>(rec + 128);
+    const bool b0 = gf_ld32(row + (t4.x & 0xffffu)) > t4.x;
+    const uint32_t n1 = b0 ? t4.z : t4.y;
+    uint32_t o = b0 ? 32u : 0u;
+    gnx_add_if_gt(o, gf_ld32(row + (n1 & 0xffffu)), n1, 16u);
+    const uint32_t n2 = gf_ld32(rec + o);
+    gnx_add_if_gt(o, gf_ld32(row + (n2 & 0xffffu)), n2, 8u);
+    const uint32_t n3 = gf_ld32(rec + 4 + o);
+    gnx_add_if_gt(o, gf_ld32(row + (n3 & 0xffffu)), n3, 4u);
+    return *reinterpret_cast<const float*>(rec + 64 + o);
+}
+
+// NCH (row, class) tasks of one thread walked as independent chains: task = first + k * GF_TEAM, numbered class-major
+// (class = task / nrows2, row = task % nrows2), so the lanes of a warp sit on the same tree and on consecutive rows.
+// Chains behind the last task walk the last task again (branch-free) and store nothing.
+template <int NCH>
+__device__ __forceinline__ void gf_walk_tasks(const unsigned char* __restrict__ st_b, int hap_bytes, int row_bytes,
+                                              const unsigned char* __restrict__ recs, int A, int rounds, int nrows, int first,
+                                              int ntask, float* __restrict__ margbuf) {
+    const unsigned char* rowp[NCH];
+    const unsigned char* rec[NCH];
+    int slot[NCH];
+    float ps[NCH];
+    const int nrows2 = 2 * nrows;
+#pragma unroll
+    for (int k = 0; k < NCH; k++) {
+        const int task = first + k * GF_TEAM;
+        const int tk = min(task, ntask - 1);
+        const int c = tk / nrows2, hr = tk - c * nrows2;
+        const int h = hr / nrows, rr = hr - h * nrows;
+        rowp[k] = st_b + h * hap_bytes + rr * row_bytes;
+        rec[k] = recs + c * GF_REC;
+        slot[k] = (task < ntask) ? hr * A + c : -1;
+        ps[k] = 0.f;
+    }
+    const int round_bytes = A * GF_REC;
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+        for (int k = 0; k < NCH; k++) {
+            ps[k] = GNX_FADD(ps[k], gf_tree(rowp[k], rec[k]));
+            rec[k] += round_bytes;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; k++)
+        if (slot[k] >= 0) margbuf[slot[k]] = ps[k];
+}
+
 template <int AT>
-__global__ void __launch_bounds__(3 * GF_TEAM, 1)
-gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t forest_bytes, GfArgs g) {
+__global__ void __launch_bounds__(GF_MAX_TEAMS * GF_TEAM, 1)
+gnofix_kernel(GbtDev m, const unsigned char* __restrict__ block_img, const uint4* __restrict__ tops_g, GfArgs g) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int A = AT ? AT : m.A;
     constexpr int AMAX = AT ? AT : GBT_MAX_A;
+    // the forest as one 144-byte record per tree, from the block image (block u32 [T][16] | leaves f32 [T][16]) and the tops
     {
-        const uint4* src = reinterpret_cast<const uint4*>(forest_img);
+        const uint4* blk = reinterpret_cast<const uint4*>(block_img);
+        const uint4* lvs = reinterpret_cast<const uint4*>(block_img + (size_t)m.T * RK_BLOCK * 4);
         uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < m.T * 9; i += blockDim.x) {
+            const int t = i / 9, q = i - t * 9;
+            dst[i] = q < 4 ? __ldg(blk + t * 4 + q) : (q < 8 ? __ldg(lvs + t * 4 + (q - 4)) : __ldg(tops_g + t));
+        }
     }
     __syncthreads();
-    const uint32_t* lower_s = reinterpret_cast<const uint32_t*>(smem);
-    const float* leaves_s = reinterpret_cast<const float*>(smem + (size_t)m.T * RK_LOWER * 4);
-    const uint4* top_s = reinterpret_cast<const uint4*>(smem + (size_t)m.T * (RK_LOWER + RK_LEAVES) * 4);
+    const unsigned char* recs = smem;
+    const size_t forest_bytes = (size_t)m.T * GF_REC;
 
     const int team = threadIdx.x / GF_TEAM, tid = threadIdx.x % GF_TEAM;
     const int W = g.W, S = m.S, T = m.T, ast = m.astride, nw = g.nw;
@@ -98,8 +171,8 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
     uint32_t* st = reinterpret_cast<uint32_t*>(tb);                 // [2][NB][ast]
     uint32_t* cand = st + 2 * NB * ast;                              // [2][S][ast]  (switched m, switched p)
     float* leafbuf = reinterpret_cast<float*>(cand + 2 * S * ast);   // [4][T]
-    uint32_t* hist = reinterpret_cast<uint32_t*>(leafbuf + 4 * T);   // [max_it][nw]
-    uint32_t* trk = hist + (size_t)g.max_it * nw;                    // [nw]
+    uint32_t* trk = reinterpret_cast<uint32_t*>(leafbuf + g.leaf_words);   // [nw]
+    uint32_t* hist = g.hist + ((size_t)blockIdx.x * g.teams + team) * (size_t)g.max_it * nw;   // [max_it][nw], global
     uint32_t* dif = trk + nw;                                        // [nw]
     uint32_t* rej = dif + nw;                                        // [nw] check at w rejected, scope unchanged since
     float* marg = reinterpret_cast<float*>(rej + nw);                // [4][GBT_MAX_A]
@@ -184,17 +257,25 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
                 }
                 team_sync(team);
                 // ---- 4 rows x T trees (smoother.model.predict_proba, gnofix.py:157) --------
+                // 64 threads per row, four independent trees in flight per thread
                 {
                     const int r = tid >> 6, q = tid & 63;
                     const unsigned char* row = reinterpret_cast<const unsigned char*>(
                         r < 2 ? st + (r * NB + sj) * ast : cand + ((r - 2) * S) * ast);
-                    for (int t = q; t < T; t += 64)
-                        leafbuf[r * T + t] = gbt_rank_tree(row, top_s[t], lower_s + t * RK_LOWER, leaves_s + t * RK_LEAVES);
+                    for (int t0 = q; t0 < T; t0 += 256) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) v[j] = gf_tree(row, recs + (size_t)min(t0 + 64 * j, T - 1) * GF_REC);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (t0 + 64 * j < T) leafbuf[r * T + t0 + 64 * j] = v[j];
+                    }
                 }
                 team_sync(team);
                 if (tid < 4 * A) {
                     const int r = tid / A, c = tid - r * A;
                     float ps = 0.f;
+#pragma unroll 4
                     for (int rd = 0; rd < rounds; rd++) ps = GNX_FADD(ps, leafbuf[r * T + rd * A + c]);
                     marg[r * GBT_MAX_A + c] = GNX_FADD(__ldg(m.base + c), ps);
                 }
@@ -252,20 +333,63 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ forest_img, size_t for
                     }
                 }
                 team_sync(team);
-                // rows straddling w: re-evaluate (Smoother.predict, smooth.py:58-61)
-                // (ncu source view: this loop is 70 % of the kernel's instructions and the barrier behind it 31 % of
-                // its stall samples; splitting the work into (row, class) tasks pulled from a team counter keeps all
-                // 8 warps busy but measured the same 357 ms in an in-process A/B -- the SM's issue slots are shared
-                // with the other two teams, so balance inside one team does not shorten the whole)
+                // rows straddling w: re-evaluate (Smoother.predict, smooth.py:58-61).  The class sums of a row are
+                // independent of each other (tree t feeds class t % A), so the unit of work is (row, class): 2 * nrows * A
+                // <= 1036 tasks of T / A trees over the team's 256 threads, GF_CH of them walked at once by a thread as
+                // independent chains -- all eight warps issue, where the row-per-thread form left three of them (and
+                // the lanes of a fifth) waiting at the barrier.  Tasks are numbered class-major, so the lanes of a warp
+                // sit on the same tree (its top is one broadcast load) and on consecutive rows.
                 const int nrows = r_hi - r_lo + 1;
-                for (int task = tid; task < 2 * nrows; task += GF_TEAM) {
-                    const int h = task / nrows, rr = task - h * nrows;
-                    const unsigned char* row = reinterpret_cast<const unsigned char*>(st + (h * NB + rr) * ast);
-                    float psum[AMAX];
-                    gbt_rank_walk<AT>(A, row, top_s, lower_s, leaves_s, rounds, psum);
-                    int32_t lab;
-                    gbt_finish<AT>(m, psum, nullptr, &lab);
-                    Ys[h * W + r_lo + rr] = (signed char)lab;
+                const unsigned char* st_b = reinterpret_cast<const unsigned char*>(st);
+                if (g.split) {
+                    float* margbuf = leafbuf;                       // [2 * nrows][A]
+                    const int ntask = 2 * nrows * A;
+                    const int warp0 = tid & ~31;
+                    for (int tb0 = 0; tb0 < ntask; tb0 += GF_CH * GF_TEAM) {
+                        // chains that hold a task for some lane of this warp (warp-uniform)
+                        const int left = ntask - tb0 - warp0;
+                        const int nlive = left <= 0 ? 0 : min(GF_CH, (left + GF_TEAM - 1) / GF_TEAM);
+                        const int first = tb0 + tid;
+                        switch (nlive) {
+                            case 5: gf_walk_tasks<5>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
+                            case 4: gf_walk_tasks<4>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
+                            case 3: gf_walk_tasks<3>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
+                            case 2: gf_walk_tasks<2>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
+                            case 1: gf_walk_tasks<1>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
+                            default: break;
+                        }
+                    }
+                    team_sync(team);
+                    for (int task = tid; task < 2 * nrows; task += GF_TEAM) {
+                        const int h = task / nrows, rr = task - h * nrows;
+                        float psum[AMAX];
+#pragma unroll
+                        for (int c = 0; c < AMAX; c++)
+                            if (c < A) psum[c] = margbuf[task * A + c];
+                        int32_t lab;
+                        gbt_finish<AT>(m, psum, nullptr, &lab);
+                        Ys[h * W + r_lo + rr] = (signed char)lab;
+                    }
+                } else {
+                    // one thread per row, its A class sums as A chains (cross-check: GNX_GNOFIX_SPLIT=0)
+                    for (int task = tid; task < 2 * nrows; task += GF_TEAM) {
+                        const int h = task / nrows, rr = task - h * nrows;
+                        const unsigned char* row = st_b + ((h * NB + rr) * ast) * 4;
+                        float psum[AMAX];
+#pragma unroll
+                        for (int c = 0; c < AMAX; c++) psum[c] = 0.f;
+                        const unsigned char* rec = recs;
+#pragma unroll 1
+                        for (int rd = 0; rd < rounds; rd++) {
+#pragma unroll
+                            for (int c = 0; c < AMAX; c++)
+                                if (c < A) psum[c] = GNX_FADD(psum[c], gf_tree(row, rec + c * GF_REC));
+                            rec += A * GF_REC;
+                        }
+                        int32_t lab;
+                        gbt_finish<AT>(m, psum, nullptr, &lab);
+                        Ys[h * W + r_lo + rr] = (signed char)lab;
+                    }
                 }
                 team_sync(team);
             }
@@ -386,25 +510,35 @@ extern "C" int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_
         GNX_CUDA(cudaMemsetAsync(diff, 0xff, db, st));  // no X: treat every block as differing (tracker equality)
 
     const int NB = 2 * S - 1, ast = m->d.astride;
-    size_t team_bytes = (size_t)2 * NB * ast * 4 + (size_t)2 * S * ast * 4 + (size_t)4 * T * 4 + (size_t)max_it * nw * 4 + (size_t)3 * nw * 4 +
+    GNX_REQUIRE(m->block_forest != nullptr, "gnx_gnofix: the forest has no block image");
+    const size_t img_bytes = (size_t)T * GF_REC, top_bytes = 0;
+    const size_t leaf_words = std::max<size_t>((size_t)4 * T, (size_t)2 * (S - 1) * A);   // check leaves / re-smoothing margins
+    size_t team_bytes = (size_t)2 * NB * ast * 4 + (size_t)2 * S * ast * 4 + leaf_words * 4 + (size_t)3 * nw * 4 +
                         (size_t)(8 * GBT_MAX_A + 4) * 4 + 16 + (size_t)2 * W;
     team_bytes = (team_bytes + 15) & ~size_t(15);
     const size_t smem_max = 227 * 1024;
-    int teams = 3;
-    while (teams > 1 && m->rank_forest_bytes + teams * team_bytes > smem_max) teams--;
-    GNX_REQUIRE(m->rank_forest_bytes + teams * team_bytes <= smem_max, "gnx_gnofix: W=%d / forest too large for shared memory", W);
-    const size_t smem = m->rank_forest_bytes + teams * team_bytes;
+    int teams = GF_MAX_TEAMS;
+    {
+        const char* et = getenv("GNX_GNOFIX_TEAMS");   // A/B knob
+        if (et && atoi(et) >= 1 && atoi(et) <= GF_MAX_TEAMS) teams = atoi(et);
+    }
+    while (teams > 1 && img_bytes + top_bytes + teams * team_bytes > smem_max) teams--;
+    GNX_REQUIRE(img_bytes + top_bytes + teams * team_bytes <= smem_max, "gnx_gnofix: W=%d / forest too large for shared memory", W);
+    const size_t smem = img_bytes + top_bytes + teams * team_bytes;
+    const int grid = (int)std::min<int64_t>(ceil_div(n_ind, teams), (int64_t)sm_count());
+    uint32_t* hist = nullptr;
+    GNX_CUDA(cudaMallocAsync((void**)&hist, (size_t)grid * teams * max_it * nw * sizeof(uint32_t), st));
     const char* em = getenv("GNX_GNOFIX_MEMO");
+    const char* es = getenv("GNX_GNOFIX_SPLIT");
     static unsigned long long* d_stats = nullptr;   // profiling counters of the last call on this process
     if (!d_stats) GNX_CUDA(cudaMalloc((void**)&d_stats, 4 * sizeof(unsigned long long)));
     GNX_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
     g_gnofix_stats = d_stats;
-    GfArgs g{ranks, diff, trk, Y_dev, tracker_dev, counter, n_ind, W, nw, max_it, teams, team_bytes, d_stats, (em && em[0] == '0') ? 0 : 1};
-    const int grid = (int)std::min<int64_t>(ceil_div(n_ind, teams), (int64_t)sm_count());
+    GfArgs g{ranks, diff, trk, hist, Y_dev, tracker_dev, counter, n_ind, W, nw, max_it, teams, team_bytes, (int)leaf_words, d_stats, (em && em[0] == '0') ? 0 : 1, (es && es[0] == '0') ? 0 : 1};
 #define CALLG(AT)                                                                                                  \
     do {                                                                                                           \
         GNX_CUDA(cudaFuncSetAttribute(gnofix_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gnofix_kernel<AT><<<grid, teams * GF_TEAM, smem, st>>>(m->d, m->rank_forest, m->rank_forest_bytes, g);     \
+        gnofix_kernel<AT><<<grid, teams * GF_TEAM, smem, st>>>(m->d, m->block_forest, m->d.top, g);                \
     } while (0)
     switch (A) {
         case 2: CALLG(2); break;
@@ -418,6 +552,7 @@ extern "C" int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_
     }
 #undef CALLG
     GNX_CUDA(cudaGetLastError());
+    GNX_CUDA(cudaFreeAsync(hist, st));
     if (X_dev)
         gnofix_apply_kernel<<<(unsigned)n_ind, 256, 0, st>>>(X_dev, ldX, C, B_dev, W, A, nw, ws, trk);
     else

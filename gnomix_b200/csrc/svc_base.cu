@@ -217,8 +217,9 @@ __device__ __forceinline__ void svc_word(SvcPair& s, uint32_t nz, int base, int 
     const int t1 = __popc(z & (nz - 1u));                 // matches before the first mismatch (32 when there is none)
     const int L = base + t1 - s.start;
     const bool closed = nz != 0u;
-    // branch-free: entry 0 of the run table is 0 (gb = its shared address)
-    s.k += svc_lds_s32(gb + 4u * (uint32_t)((closed && L >= min_big) ? L : 0));
+    // branch-free: the run table is 0 below the first long length and at entry 0 (gb = its shared address); a closing
+    // run has 0 <= L <= window length
+    s.k += svc_lds_s32(gb + 4u * (uint32_t)(closed ? L : 0));
     const int ns = base + 32 - __clz(nz);                 // position behind the last mismatch
     s.start = closed ? ns : s.start;
     // carry-save tree over the inputs z, r4, r8 of four consecutive words
@@ -285,24 +286,26 @@ __device__ __forceinline__ void svc_block(SvcPair (&st)[2][SB], const uint32_t* 
 
 constexpr int SVC_SB = 2;   // support vectors a warp walks at once (x 2 queries per lane)
 
-__global__ void __launch_bounds__(SVC_THREADS, 3)
+// SVC_CCHUNK support vectors per CTA, compiled for SVC_CCTAS CTAs per SM (instantiated as <48, 3>: 80 registers)
+template <int SVC_CCHUNK, int SVC_CCTAS>
+__global__ void __launch_bounds__(SVC_THREADS, SVC_CCTAS)
 svc_kernel_csa(SvcDev m, const SvcWin* __restrict__ wins, int w0, const uint32_t* __restrict__ QP, int64_t qp_words, int64_t N,
                int32_t* __restrict__ Kt, int64_t ldK, int64_t kt_win_stride, int32_t* __restrict__ Krow) {
     extern __shared__ __align__(16) uint32_t sm[];
     const SvcWin w = wins[w0 + blockIdx.z];
-    const int s0 = blockIdx.y * SVC_CHUNK;
+    const int s0 = blockIdx.y * SVC_CCHUNK;
     if (s0 >= w.nsv) return;
     const int nw = w.nw;
     const int nblk = (nw + 1 + 3) / 4;   // the window's words plus at least one all-mismatch word behind it
     const int rs = (4 * nblk) | 1;       // row stride in words: whole blocks are addressable, odd for the banks
     uint32_t* qp = sm;                               // [64][2][rs]
-    uint32_t* sp = qp + (size_t)SVC_Q * 2 * rs;      // [SVC_CHUNK][2][rs]
-    int32_t* gb = reinterpret_cast<int32_t*>(sp + (size_t)SVC_CHUNK * 2 * rs);   // [len + 1]
+    uint32_t* sp = qp + (size_t)SVC_Q * 2 * rs;      // [SVC_CCHUNK][2][rs]
+    int32_t* gb = reinterpret_cast<int32_t*>(sp + (size_t)SVC_CCHUNK * 2 * rs);   // [len + 1]
     const uint32_t gb_s = (uint32_t)__cvta_generic_to_shared(gb);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n0 = (int64_t)blockIdx.x * SVC_Q;
     if (Kt) Kt += (int64_t)blockIdx.z * kt_win_stride;
-    const int ns = min(SVC_CHUNK, w.nsv - s0);
+    const int ns = min(SVC_CCHUNK, w.nsv - s0);
     {
         const int64_t wi0 = w.lo >> 5;
         const int sh = (int)(w.lo & 31);
@@ -317,7 +320,7 @@ svc_kernel_csa(SvcDev m, const SvcWin* __restrict__ wins, int w0, const uint32_t
             qp[i] = v;
         }
         const uint32_t* src = w.planes + (size_t)s0 * 2 * nw;
-        for (int i = threadIdx.x; i < SVC_CHUNK * 2 * rs; i += SVC_THREADS) {
+        for (int i = threadIdx.x; i < SVC_CCHUNK * 2 * rs; i += SVC_THREADS) {
             const int row = i / rs, j = i - row * rs;
             sp[i] = (row < ns * 2 && j < nw) ? __ldg(src + (size_t)row * nw + j) : 0u;
         }
@@ -328,7 +331,7 @@ svc_kernel_csa(SvcDev m, const SvcWin* __restrict__ wins, int w0, const uint32_t
     const int min_big = m.min_big;
     const int nfull = (nw - 1) / 4;      // blocks whose four words all lie before the window's last word
     constexpr int SB = SVC_SB;
-    for (int sb = warp * (SVC_CHUNK / 8); sb < (warp + 1) * (SVC_CHUNK / 8) && sb < ns; sb += SB) {
+    for (int sb = warp * (SVC_CCHUNK / 8); sb < (warp + 1) * (SVC_CCHUNK / 8) && sb < ns; sb += SB) {
         SvcPair st[2][SB];
 #pragma unroll
         for (int a = 0; a < 2; a++)
@@ -710,11 +713,14 @@ static int svc_launch_csa(const gnx_svc_t* m, int w0, int g, const uint32_t* QP,
     }
     if (nsv_max == 0) return 0;
     const size_t rs_max = (size_t)((4 * ((nw_max + 1 + 3) / 4)) | 1);
-    const size_t smem = ((size_t)SVC_Q * 2 * rs_max + (size_t)SVC_CHUNK * 2 * rs_max + (size_t)len_max + 2) * 4;
+    // <48, 3>: 80 registers, 3 CTAs per SM.  <32, 4> (64 registers, 4 CTAs) measured 13 % slower: the kernel is bound by
+    // the integer pipe, not by latency, and the smaller chunk stages the 64 queries once per 32 instead of 48 vectors
+    constexpr int chunk = 48;
+    const size_t smem = ((size_t)SVC_Q * 2 * rs_max + (size_t)chunk * 2 * rs_max + (size_t)len_max + 2) * 4;
     GNX_REQUIRE(smem <= 227 * 1024, "gnx_svc: window of %d SNPs too long for shared memory", len_max);
-    GNX_CUDA(cudaFuncSetAttribute(svc_kernel_csa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)ceil_div(N, SVC_Q), (unsigned)ceil_div(nsv_max, SVC_CHUNK), (unsigned)g);
-    svc_kernel_csa<<<grid, SVC_THREADS, smem, st>>>(m->d, m->d_win, w0, QP, svc_qp_words(m), N, Kt, ldK, kt_win, Krow);
+    dim3 grid((unsigned)ceil_div(N, SVC_Q), (unsigned)ceil_div(nsv_max, chunk), (unsigned)g);
+    GNX_CUDA(cudaFuncSetAttribute(svc_kernel_csa<chunk, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    svc_kernel_csa<chunk, 3><<<grid, SVC_THREADS, smem, st>>>(m->d, m->d_win, w0, QP, svc_qp_words(m), N, Kt, ldK, kt_win, Krow);
     GNX_CUDA(cudaGetLastError());
     return 0;
 }
