@@ -89,8 +89,7 @@ __device__ __forceinline__ uint32_t gf_ld32(const unsigned char* p) { return *re
 // nodes read from the record as one 16-byte load.  (The row kernel takes the tops from the parameter bank, free there because
 // all warps of its CTA are on the same tree; the teams of this kernel are not, the indexed constant loads queue up: measured
 // 17 % slower than shared-memory tops.)
-__device__ __forceinline__ float gf_tree(const unsigned char* __restrict__ row, const unsigned char* __restrict__ rec) {
-    const uint4 t4 = *reinterpret_cast<const uint4*>(rec + 128);
+__device__ __forceinline__ float gf_tree_t(const unsigned char* __restrict__ row, const unsigned char* __restrict__ rec, const uint4 t4) {
     const bool b0 = gf_ld32(row + (t4.x & 0xffffu)) > t4.x;
     const uint32_t n1 = b0 ? t4.z : t4.y;
     uint32_t o = b0 ? 32u : 0u;
@@ -101,42 +100,39 @@ __device__ __forceinline__ float gf_tree(const unsigned char* __restrict__ row, 
     gnx_add_if_gt(o, gf_ld32(row + (n3 & 0xffffu)), n3, 4u);
     return *reinterpret_cast<const float*>(rec + 64 + o);
 }
+__device__ __forceinline__ float gf_tree(const unsigned char* __restrict__ row, const unsigned char* __restrict__ rec) {
+    return gf_tree_t(row, rec, *reinterpret_cast<const uint4*>(rec + 128));
+}
 
-// NCH (row, class) tasks of one thread walked as independent chains: task = first + k * GF_TEAM, numbered class-major
-// (class = task / nrows2, row = task % nrows2), so the lanes of a warp sit on the same tree and on consecutive rows.
-// Chains behind the last task walk the last task again (branch-free) and store nothing.
+// Re-smoothing unit of a warp: ONE class and 32 * NCH rows -- lane l walks rows hr0 + 32 k (k < NCH) as independent chains
+// through the class's T / A trees.  Every chain of the warp is on the same tree: its record pointer is advanced once and its
+// top is one 16-byte broadcast load per tree.  Chains behind the last row walk the last row again (branch-free) and store
+// nothing.  hr numbers the rows of both haplotypes (hr = h * nrows + rr).
 template <int NCH>
-__device__ __forceinline__ void gf_walk_tasks(const unsigned char* __restrict__ st_b, int hap_bytes, int row_bytes,
-                                              const unsigned char* __restrict__ recs, int A, int rounds, int nrows, int first,
-                                              int ntask, float* __restrict__ margbuf) {
+__device__ __forceinline__ void gf_walk_class(const unsigned char* __restrict__ st_b, int hap_bytes, int row_bytes,
+                                              const unsigned char* __restrict__ rec, int A, int c, int rounds, int nrows, int hr0,
+                                              float* __restrict__ margbuf) {
     const unsigned char* rowp[NCH];
-    const unsigned char* rec[NCH];
-    int slot[NCH];
     float ps[NCH];
     const int nrows2 = 2 * nrows;
 #pragma unroll
     for (int k = 0; k < NCH; k++) {
-        const int task = first + k * GF_TEAM;
-        const int tk = min(task, ntask - 1);
-        const int c = tk / nrows2, hr = tk - c * nrows2;
-        const int h = hr / nrows, rr = hr - h * nrows;
+        const int hr = min(hr0 + 32 * k, nrows2 - 1);
+        const int h = hr >= nrows ? 1 : 0, rr = hr - h * nrows;
         rowp[k] = st_b + h * hap_bytes + rr * row_bytes;
-        rec[k] = recs + c * GF_REC;
-        slot[k] = (task < ntask) ? hr * A + c : -1;
         ps[k] = 0.f;
     }
     const int round_bytes = A * GF_REC;
 #pragma unroll 1
     for (int rd = 0; rd < rounds; rd++) {
+        const uint4 t4 = *reinterpret_cast<const uint4*>(rec + 128);
 #pragma unroll
-        for (int k = 0; k < NCH; k++) {
-            ps[k] = GNX_FADD(ps[k], gf_tree(rowp[k], rec[k]));
-            rec[k] += round_bytes;
-        }
+        for (int k = 0; k < NCH; k++) ps[k] = GNX_FADD(ps[k], gf_tree_t(rowp[k], rec, t4));
+        rec += round_bytes;
     }
 #pragma unroll
     for (int k = 0; k < NCH; k++)
-        if (slot[k] >= 0) margbuf[slot[k]] = ps[k];
+        if (hr0 + 32 * k < nrows2) margbuf[(hr0 + 32 * k) * A + c] = ps[k];
 }
 
 template <int AT>
@@ -334,29 +330,30 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ block_img, const uint4
                 }
                 team_sync(team);
                 // rows straddling w: re-evaluate (Smoother.predict, smooth.py:58-61).  The class sums of a row are
-                // independent of each other (tree t feeds class t % A), so the unit of work is (row, class): 2 * nrows * A
-                // <= 1036 tasks of T / A trees over the team's 256 threads, GF_CH of them walked at once by a thread as
-                // independent chains -- all eight warps issue, where the row-per-thread form left three of them (and
-                // the lanes of a fifth) waiting at the barrier.  Tasks are numbered class-major, so the lanes of a warp
-                // sit on the same tree (its top is one broadcast load) and on consecutive rows.
+                // independent of each other (tree t feeds class t % A), so the work splits into (row, class) tasks of
+                // T / A trees: a warp takes one class and up to 32 * GF_CH rows, each lane walking GF_CH rows as
+                // independent chains (gf_walk_class) -- seven or eight warps issue, where the row-per-thread form left
+                // three of them (and the lanes of a fifth) waiting at the barrier.
                 const int nrows = r_hi - r_lo + 1;
                 const unsigned char* st_b = reinterpret_cast<const unsigned char*>(st);
                 if (g.split) {
                     float* margbuf = leafbuf;                       // [2 * nrows][A]
-                    const int ntask = 2 * nrows * A;
-                    const int warp0 = tid & ~31;
-                    for (int tb0 = 0; tb0 < ntask; tb0 += GF_CH * GF_TEAM) {
-                        // chains that hold a task for some lane of this warp (warp-uniform)
-                        const int left = ntask - tb0 - warp0;
-                        const int nlive = left <= 0 ? 0 : min(GF_CH, (left + GF_TEAM - 1) / GF_TEAM);
-                        const int first = tb0 + tid;
-                        switch (nlive) {
-                            case 5: gf_walk_tasks<5>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
-                            case 4: gf_walk_tasks<4>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
-                            case 3: gf_walk_tasks<3>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
-                            case 2: gf_walk_tasks<2>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
-                            case 1: gf_walk_tasks<1>(st_b, NB * ast * 4, ast * 4, recs, A, rounds, nrows, first, ntask, margbuf); break;
-                            default: break;
+                    // units = (class, chunk of 32 * nch rows); the fewest chains per lane that fit all units on the 8 warps
+                    const int nrows2 = 2 * nrows;
+                    int nch = 1;
+                    while (nch < GF_CH && A * ((nrows2 + 32 * nch - 1) / (32 * nch)) > GF_TEAM / 32) nch++;
+                    const int chunks = (nrows2 + 32 * nch - 1) / (32 * nch);
+                    for (int u = tid >> 5; u < A * chunks; u += GF_TEAM / 32) {
+                        const int c = u / chunks, j = u - c * chunks;
+                        const int hr0 = j * 32 * nch + (tid & 31);
+                        const int nl = min(nch, (nrows2 - j * 32 * nch + 31) / 32);   // chains holding a row for some lane
+                        const unsigned char* rec = recs + c * GF_REC;
+                        switch (nl) {
+                            case 5: gf_walk_class<5>(st_b, NB * ast * 4, ast * 4, rec, A, c, rounds, nrows, hr0, margbuf); break;
+                            case 4: gf_walk_class<4>(st_b, NB * ast * 4, ast * 4, rec, A, c, rounds, nrows, hr0, margbuf); break;
+                            case 3: gf_walk_class<3>(st_b, NB * ast * 4, ast * 4, rec, A, c, rounds, nrows, hr0, margbuf); break;
+                            case 2: gf_walk_class<2>(st_b, NB * ast * 4, ast * 4, rec, A, c, rounds, nrows, hr0, margbuf); break;
+                            default: gf_walk_class<1>(st_b, NB * ast * 4, ast * 4, rec, A, c, rounds, nrows, hr0, margbuf); break;
                         }
                     }
                     team_sync(team);
