@@ -379,6 +379,8 @@ def config_gnofix(X, ld, base, smooth, geom, n_haps):
     _lib.check(lib.gnx_lr_predict(base.handle(), Xc.data_ptr(), N, ld, B.data_ptr(), st))
     ns = 2   # individuals checked against the oracle restatement of the reference's gnofix
     X_in, B_in = Xc[:2 * ns, :C].cpu().numpy(), B[:2 * ns].cpu().numpy()
+    nw_ = min(N, 512)   # warm-up on copies of a few pairs (module load, pool growth), then ONE timed pass over all
+    phase_device(smooth, Xc[:nw_].clone(), ld, C, B[:nw_].clone())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -404,6 +406,56 @@ def config_gnofix(X, ld, base, smooth, geom, n_haps):
             "accepted_switches": int(stats[3]), "net_switches_per_individual": sw / (N // 2),
             "algorithmic_bytes": N * (2 * C + 2 * W * A * 4 + 2 * W * 4),
             "parity_vs_oracle": {"individuals": ns, "labels_equal": ok_y, "tracker_equal": ok_t, "X_phased_equal": ok_x}}
+
+
+def config_crf_gnofix(X, ld, base, geom, n_haps):
+    """BASELINE configs[4] as worded ("CRF smoother + Gnofix"): AN EXTENSION, the reference refuses the combination
+    (src/model.py:194) -- gnx_gnofix_crf, defined in include/gnx.h; the checker is the oracle's restatement of the
+    reference's gnofix control flow with the oracle's CRF plugged in (no reference oracle exists)."""
+    import torch
+    from gnomix_b200 import _lib
+    from gnomix_b200.gnofix import phase_device_crf
+    from gnomix_b200.smooth import CRF_Smoother, CRFModel
+    from oracle import c_oracle as co, np_oracle as npo
+    C, M, A, S, morgans = geom
+    W, N = C // M, n_haps
+    lib, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    Xc = X[:N].clone()
+    plant_switches(Xc, ld, C, W)
+    crf = CRF_Smoother(n_windows=W, num_ancestry=A, smooth_window_size=S)
+    rng = np.random.default_rng(3)
+    crf.model = CRFModel(np.eye(A) * 4.0 + rng.normal(0, 0.2, (A, A)), np.eye(A) * 3.0 + rng.normal(0, 0.2, (A, A)))
+    B = torch.empty((N, W, A), dtype=torch.float64, device="cuda")
+    _lib.check(lib.gnx_lr_predict_f64(base.handle(), Xc.data_ptr(), N, ld, B.data_ptr(), st))
+    ns = 2
+    X_in, B_in = Xc[:2 * ns, :C].cpu().numpy(), B[:2 * ns].cpu().numpy()
+    nw_ = min(N, 128)
+    phase_device_crf(crf, Xc[:nw_].clone(), ld, C, B[:nw_].clone())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    Y, trk = phase_device_crf(crf, Xc, ld, C, B, want_tracker=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t6 = e0.elapsed_time(e1)
+    stats = np.zeros(4, dtype=np.int64)
+    lib.gnx_gnofix_crf_last_stats(stats.ctypes.data)
+    sw = int((trk[0::2, 1:] != trk[0::2, :-1]).sum().item())
+    ok_y = ok_x = ok_t = True
+    Yh, Th, Xh = Y[:2 * ns].cpu().numpy(), trk[:2 * ns].cpu().numpy(), Xc[:2 * ns, :C].cpu().numpy()
+    for i in range(ns):
+        X_m, X_p, Y_m, Y_p, t = npo.gnofix_crf_extension(X_in[2 * i], X_in[2 * i + 1], B_in[2 * i:2 * i + 2], S, crf.model.state_w,
+                                                         crf.model.trans_w, crf_smooth_fn=co.crf_smooth)
+        ok_y &= bool(np.array_equal(Yh[2 * i:2 * i + 2], np.array([Y_m, Y_p])))
+        ok_t &= bool(np.array_equal(Th[2 * i:2 * i + 2], t))
+        ok_x &= bool(np.array_equal(Xh[2 * i:2 * i + 2], np.array([X_m, X_p])))
+    return {"workload": "chr1 W=%d A=%d, logistic (float64) + CRF + Gnofix, %d individuals resident, 20 planted switch errors each" % (W, A, N // 2),
+            "extension": "no reference behaviour (src/model.py:194 refuses a CRF smoother): the reference's gnofix control flow with "
+                         "smoother.predict := argmax CRF marginals, smoother.model.predict_proba(scope) := CRF marginal at the scope's centre",
+            "K6c_ms": t6, "individuals_per_s": (N // 2) / (t6 * 1e-3), "rounds": int(stats[0]), "checks": int(stats[1]),
+            "accepted_switches": int(stats[2]), "iterations": int(stats[3]), "net_switches_per_individual": sw / (N // 2),
+            "parity_vs_oracle": {"individuals": ns, "labels_equal": ok_y, "tracker_equal": ok_t, "X_phased_equal": ok_x,
+                                 "oracle": "oracle/np_oracle.py::gnofix_crf_extension (restated control flow + the oracle's CRF; not a reference output)"}}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -712,7 +764,8 @@ def run_ours(args):
         for name, fn in (("cfg2_chr22_m1000_lr_xgb", lambda: config_chr22(peak)),
                          ("cfg4_chr1_covrsk_base", lambda: config_covrsk(X, ld, geom, min(N, args.covrsk_haps), peak)),
                          ("cfg5_chr1_lr_crf", lambda: config_crf(X, ld, base, geom, n_c)),
-                         ("cfg5_chr1_lr_xgb_gnofix", lambda: config_gnofix(X, ld, base, smooth, geom, n_c))):
+                         ("cfg5_chr1_lr_xgb_gnofix", lambda: config_gnofix(X, ld, base, smooth, geom, n_c)),
+                         ("cfg5_chr1_lr_crf_gnofix_extension", lambda: config_crf_gnofix(X, ld, base, geom, min(n_c, args.crf_gnofix_haps)))):
             torch.cuda.empty_cache()
             try:
                 cfgs[name] = fn()
@@ -728,6 +781,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--crf-gnofix-haps", type=int, default=4000, help="haplotypes of the CRF + Gnofix extension config")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--haps", type=int, default=50_000, help="haplotypes per GPU")

@@ -48,6 +48,8 @@ _SIGS = {
     "gnx_cal_model_destroy": (None, [c_vp]),
     "gnx_calibrate": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp]),
     "gnx_gnofix_last_stats": (C.c_int, [c_vp]),
+    "gnx_gnofix_crf": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_i64, c_vp, c_i64, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "gnx_gnofix_crf_last_stats": (C.c_int, [c_vp]),
     "gnx_infer_host": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64]),
     "gnx_infer_host_ex": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64]),
     "gnx_vcf_to_haplotypes_packed": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, C.c_int]),

@@ -168,11 +168,15 @@ class Gnomix:
                 if type(val) in [int, float, str, bool, np.float64, np.float32, np.int64]:
                     f.write("{}\t{}\n".format(attr, val))
 
-    def phase(self, X, B=None, verbose=False, want_tracker=False):
+    def phase(self, X, B=None, verbose=False, want_tracker=False, crf_extension=False):
         """Gnofix over all individuals (src/model.py:188-214): one launch instead of a
-        Python loop over individuals."""
+        Python loop over individuals.  `crf_extension=True` additionally admits a CRF smoother: the reference
+        refuses that combination (its assert below), the extension is defined in include/gnx.h (gnx_gnofix_crf)
+        and has no reference oracle."""
         assert self.smooth is not None, "Smoother is not trained, returning original haplotypes"
-        assert self.smooth.gnofix, "Type of Smoother ({}) does not currently support re-phasing".format(self.smooth)
+        from .smooth import CRFModel
+        is_crf_ext = crf_extension and isinstance(getattr(self.smooth, "model", None), CRFModel)
+        assert self.smooth.gnofix or is_crf_ext, "Type of Smoother ({}) does not currently support re-phasing".format(self.smooth)
         from .gnofix import phase_all
         return phase_all(self, X, B=B, verbose=verbose, want_tracker=want_tracker)
 

@@ -174,6 +174,25 @@ int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float*
 int gnx_gnofix_last_stats(int64_t* out4);
 
 /* ---------------------------------------------------------------------------
+ * K6c  Gnofix with the CRF smoother -- AN EXTENSION WITHOUT A REFERENCE ORACLE.
+ * The reference refuses this combination (src/model.py:194 asserts `smooth.gnofix`, set by
+ * XGB_Smoother only; src/Gnofix/gnofix.py:157 calls `smoother.model.predict_proba` on flattened
+ * S-window rows, which a chain CRF does not have).  Defined as the
+ * reference's gnofix control flow (src/Gnofix/gnofix.py:58-208, default arguments) with
+ *   smoother.predict(B)                 := argmax of the CRF marginals of the whole chain,
+ *   smoother.model.predict_proba(scope) := the CRF marginal at the centre of the S-window scope
+ *                                          run as a chain of its own.
+ * X_dev [2n, ldX] int8 (nullable) and B_dev [2n, W, A] FLOAT64 (what the CRF smoother reads) are
+ * updated in place; Y_dev [2n, W] int32 the final labels; tracker_dev [2n, W] int32 nullable.
+ * S odd, S <= W, max_it <= 64.  Checked against oracle/np_oracle.py::gnofix_crf_extension.
+ * ------------------------------------------------------------------------- */
+int gnx_gnofix_crf(const gnx_crf_t* m, int S, int8_t* X_dev, int64_t ldX, int64_t C, double* B_dev,
+                   int64_t n_ind, int W, int max_it, int32_t* Y_dev, int32_t* tracker_dev,
+                   void* stream);
+/* counters of the last gnx_gnofix_crf call: rounds, candidate checks, accepted switches, outer iterations */
+int gnx_gnofix_crf_last_stats(int64_t* out4);
+
+/* ---------------------------------------------------------------------------
  * K7  Calibrator.transform on smoother probabilities (+ argmax)
  * replaces: src/Smooth/Calibration.py:57-69 (per-class IsotonicRegression(out_of_bounds=
  *           "clip").transform) and the normalisation of lines 24-39, as called from

@@ -608,3 +608,27 @@ def gnofix_default(X_m, X_p, B, S, predict_rows, smooth_predict, max_it=50):
                     X_p[i:] = tmp[i:]
                     Y_m, Y_p = smooth_predict(B).reshape(2, W)
     return X_m, X_p, Y_m, Y_p, np.array([trk_m, trk_p])
+
+
+def gnofix_crf_extension(X_m, X_p, B, S, state_w, trans_w, crf_smooth_fn=None, max_it=50):
+    """Gnofix with the CRF smoother -- AN EXTENSION, NO REFERENCE ORACLE: the reference refuses the combination
+    (src/model.py:194; src/Gnofix/gnofix.py:157 needs `smoother.model.predict_proba` on flattened S-window rows).
+    Defined as SURVEY.md section 8a row G words it: the reference's gnofix control flow (`gnofix_default` above, which
+    is pinned to the reference's own gnofix) with
+        smooth_predict(B[2, W, A])  = argmax of the CRF marginals of each whole chain (CRF_Smoother.predict),
+        predict_rows(rows[k, S*A])  = the CRF marginal at the centre item (S - 1) // 2 of each scope run as a chain
+                                      of S items of its own.
+    crf_smooth_fn(B[n, T, A], state_w, trans_w) -> (marginals, labels); default: `crf_smooth` of this module
+    (tests pass the C twin, same bits).  B is float64, as the CRF smoother reads it."""
+    fn = crf_smooth_fn or crf_smooth
+    A = np.asarray(B).shape[-1]
+    c = (S - 1) // 2
+
+    def predict_rows(rows):
+        marg, _ = fn(np.asarray(rows, dtype=np.float64).reshape(-1, S, A), state_w, trans_w)
+        return np.asarray(marg)[:, c, :]
+
+    def smooth_predict(b):
+        return np.asarray(fn(np.asarray(b, dtype=np.float64), state_w, trans_w)[1])
+
+    return gnofix_default(X_m, X_p, np.asarray(B, dtype=np.float64), S, predict_rows, smooth_predict, max_it=max_it)
