@@ -697,9 +697,10 @@ def run_ours(args):
     k1_bytes = N * (C + W * A * 4)
     k4_bytes = N * (2 * W * A * 4 + W * 4)
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    # K4's own roofline: shared-memory wavefronts.  A depth-4 tree costs a warp 7 wavefronts (4 feature loads,
-    # 2 node loads, 1 leaf load); an SM retires one wavefront per clock.
-    k4_wavefronts = N * W * T / 32.0 * 7.0
+    # K4's own roofline: shared-memory wavefronts.  A depth-4 tree costs a warp 6.5 wavefronts per window (3 feature
+    # loads + the root's, which the two adjacent windows of a warp share through a pair word, 2 node loads, 1 leaf
+    # load); an SM retires one wavefront per clock.
+    k4_wavefronts = N * W * T / 32.0 * 6.5
     lsu_peak = N_SMS * sm_mhz * 1e6
     Wp = W + S - 1
     k4a_bytes = N * (W * A * 4 + Wp * A * 2)            # float32 B in, u16 rank tiles (reflect pad materialised) out
@@ -725,7 +726,7 @@ def run_ours(args):
     roof_k4 = {"kernel": "K4b_gbt_smooth_tile", "bound": "lsu", "achieved": k4_wavefronts / (k4b_ms * 1e-3) / 1e9,
                "peak": lsu_peak / 1e9, "unit": "G shared-memory wavefronts/s", "frac": kernels["K4b_gbt_smooth_tile"]["frac_lsu"],
                "peak_source": "148 SMs x 1 wavefront per clock x the SM clock sampled during the timed region (%.0f MHz)" % sm_mhz,
-               "algorithmic": "7 wavefronts per warp and tree (4 feature, 2 node, 1 leaf load) x N*W*T/32 warp-trees",
+               "algorithmic": "6.5 wavefronts per warp and tree (3.5 feature -- the root's load serves two adjacent windows --, 2 node, 1 leaf load) x N*W*T/32 warp-trees",
                "traffic": f4.get("dram_bytes"), "hbm": {"achieved": kernels["K4b_gbt_smooth_tile"]["gbs"], "peak": peak, "unit": "GB/s",
                                                         "frac": kernels["K4b_gbt_smooth_tile"]["frac_hbm"], "algorithmic_bytes": k4b_bytes},
                "ncu": f4 or None,

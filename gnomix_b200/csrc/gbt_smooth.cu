@@ -329,14 +329,14 @@ int gnx_gbt_model_create(gnx_gbt_t** out, int A, int S, int n_trees, const int32
         m->block_forest = static_cast<const unsigned char*>(d_b);
         m->block_forest_bytes = bimg.size() * 4;
         if (cudaMemcpy(d_b, bimg.data(), bimg.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("block image copy failed");
-        // tile image (gbt_tile.cu): node word (k << 17) | (feature << 7), so `rank << 17 > word` is the split test and
-        // `word & 0x1ff80` the byte offset of the feature in a lane-interleaved tile; one 128-byte record per tree:
+        // tile image (gbt_tile.cu): node word (k << 17) | (0x8000 + (feature << 7)), so `pair word > node word` is the
+        // split test and `word & 0x1ff80` the (biased) byte offset of the feature in a lane-interleaved tile; one 128-byte record per tree:
         // the same 16-word block, then its 16 leaves
         if (K <= GBT_TILE_MAX_K && F <= GBT_TILE_MAX_F && n_trees <= GBT_TILE_MAX_T) {
             auto conv = [&](uint32_t word) -> uint32_t {  // (k << 16 | byte offset in a rank row) -> tile word
                 const uint32_t k = word >> 16, off = (word & 0xffffu) / 4u, slot = off / (uint32_t)astride, a = off % (uint32_t)astride;
                 const uint32_t kk = (k == 0xFFFFu) ? (uint32_t)GBT_TILE_MAX_K : k;   // always-left filler: no rank exceeds it
-                return (kk << 17) | ((slot * (uint32_t)A + a) << 7);
+                return (kk << 17) | (GBT_TILE_FBIAS + ((slot * (uint32_t)A + a) << 7));
             };
             std::vector<uint32_t> timg((size_t)n_trees * 32, 0u);
             for (int t = 0; t < n_trees; t++) {

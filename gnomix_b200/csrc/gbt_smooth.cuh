@@ -12,9 +12,10 @@ constexpr int GBT_MAX_DEPTH = 8;
 constexpr int RK_THREADS = 1024;
 constexpr int RK_LOWER = 12;   // nodes 3..14 of a depth-4 heap
 constexpr int RK_LEAVES = 16;
-// tile kernel (gbt_tile.cu): node word = (k << 17) | (feature << 7)
+// tile kernel (gbt_tile.cu): node word = (k << 17) | (GBT_TILE_FBIAS + (feature << 7))
 constexpr int GBT_TILE_MAX_K = 32767;   // threshold indices (and ranks) must fit 15 bits
-constexpr int GBT_TILE_MAX_F = 1023;    // feature << 7 must stay below bit 17
+constexpr int GBT_TILE_MAX_F = 767;     // GBT_TILE_FBIAS + (feature << 7) must stay below bit 17
+constexpr uint32_t GBT_TILE_FBIAS = 0x8000u;   // added to the feature field of a tile node word (gbt_tile.cu: pair words)
 constexpr int GBT_TILE_MAX_T = 1792;    // tree tops travel in the kernel parameter bank (28 KB of the 32 KB)
 constexpr int GBT_TILE_MIN_N = 24;      // below this many haplotypes the row kernel is used (lanes = haplotypes here)
 constexpr int GBT_RANK_CELLS = 8192;    // equal cells over the threshold range (rank pass of the tile kernel)

@@ -2,21 +2,25 @@
 // (reference src/Smooth/utils.py:4-29 slide_window + src/Smooth/models.py:14-20 xgboost predict_proba +
 // src/Smooth/smooth.py:61 argmax) for batches of haplotypes.
 //
-// The walk of a depth-4 tree is four data-dependent feature loads, two node loads and one leaf load:
-// seven shared-memory wavefronts per warp and tree is the floor of any layout in which a lane owns a row,
-// and the kernel is built to sit on that floor:
+// The walk of a depth-4 tree is four data-dependent feature loads, two node loads and one leaf load: seven
+// shared-memory wavefronts per warp and tree when a lane owns a row -- six and a half here, because the two
+// adjacent windows a warp walks share the load of the root's feature (pair words, below) -- and the kernel is built
+// to sit on that floor:
 //   * lane = haplotype, warp = window.  The rank tile is lane-interleaved -- word (slot * A + a) * 32 + lane --
 //     so a feature load hits bank `lane` whatever node each lane has reached: no bank conflicts under
 //     divergence (the row kernel, lanes = windows, pays ~1.2 conflict wavefronts per tree).
-//   * node word = (k << 17) | (feature << 7): `rank << 17 > word` is the split test `!(x < thr)` and
-//     `word & 0x1ff80` is the byte offset of the feature row in the tile, so a level costs
-//     LDS node, LOP3 (mask | lane * 4), LDS feature, ISETP, predicated IADD.
+//   * tile word of slot s = rank(s) << 17 | rank(s + 1) (ranks are 15 bits), node word = (k << 17) | (0x8000 +
+//     (feature << 7)): `tile word > node word` is the split test `!(x < thr)` of the window whose feature sits in
+//     slot s -- when rank(s) == k the low halves decide, and the node's (>= 0x8000) is never below the tile word's
+//     (<= 0x7fff) -- and `word & 0x1ff80` is the byte offset of the feature row behind `tile - 0x8000`, so a level
+//     costs LDS node, LOP3 (mask | lane * 4), LDS feature, ISETP, predicated IADD.  The root of a tree tests the SAME
+//     feature in windows w and w + 1, one slot apart: one load serves both (`word << 17` is the second window's).
 //   * per tree one 128-byte record { 16-word block, 16 leaves } addressed by ONE accumulating byte offset
 //     o = 32 b0 + 16 b1 + 8 b2 + 4 b3 (level-2 node at block + o, level-3 node at block + 4 + o, leaf at
 //     leaves + o); lanes of a warp read distinct banks or the same word.
 //   * the top three nodes of every tree come from the kernel parameter bank (warp-uniform: constant cache).
-//   * a warp walks two windows at once (rows wl and wl + 32 of the tile): the uniform work per tree is
-//     shared and there are 2 * A independent dependency chains in flight.
+//   * a warp walks two adjacent windows at once (rows 2 * warp and 2 * warp + 1 of the tile): the uniform work per
+//     tree and the root's feature load are shared and there are 2 * A independent dependency chains in flight.
 // K4a turns the float32 base probabilities into their exact ranks (u16) once, written in the order the
 // tiles are staged in: R2[haplotype block][padded slot][class][32 lanes], reflect padding materialised.
 #include <math.h>
@@ -225,19 +229,25 @@ __device__ __forceinline__ uint32_t gnx_feat_off(uint32_t n, uint32_t lane4) {
     return d;
 }
 
-// One tree for one row.  rowu = shared address of the row's first tile word (warp-uniform), rowl = rowu + lane * 4,
-// lane4 = lane * 4, rec = shared address of the tree's 128-byte record (warp-uniform).
-__device__ __forceinline__ float gbt_tile_tree(uint32_t rowu, uint32_t rowl, uint32_t lane4, uint32_t t0, uint32_t t1, uint32_t t2,
-                                               uint32_t a0, uint32_t rec) {
-    const bool b0 = gnx_lds_u32(rowl + a0) > t0;
-    const uint32_t n1 = b0 ? t2 : t1;
-    uint32_t o = b0 ? 32u : 0u;
-    gnx_add_if_gt(o, gnx_lds_u32(rowu + gnx_feat_off(n1, lane4)), n1, 16u);
-    const uint32_t n2 = gnx_lds_u32(rec + o);
-    gnx_add_if_gt(o, gnx_lds_u32(rowu + gnx_feat_off(n2, lane4)), n2, 8u);
-    const uint32_t n3 = gnx_lds_u32(rec + 4u + o);
-    gnx_add_if_gt(o, gnx_lds_u32(rowu + gnx_feat_off(n3, lane4)), n3, 4u);
-    return gnx_lds_f32(rec + 64u + o);
+// One tree for the two adjacent rows of a warp.  rau / rbu = shared address of the rows' first tile word minus the bias of the
+// feature field (warp-uniform), lane4 = lane * 4, rec = shared address of the tree's 128-byte record
+// (warp-uniform).  The root's feature of row b is the low half of the pair word row a loads.
+__device__ __forceinline__ void gbt_tile_tree2(uint32_t rau, uint32_t rbu, uint32_t lane4, uint32_t t0, uint32_t t1, uint32_t t2,
+                                               uint32_t a0, uint32_t rec, float& la, float& lb) {
+    const uint32_t x0 = gnx_lds_u32(rau + (a0 + lane4));
+    const bool ba0 = x0 > t0, bb0 = (x0 << 17) > t0;
+    const uint32_t na1 = ba0 ? t2 : t1, nb1 = bb0 ? t2 : t1;
+    uint32_t oa = ba0 ? 32u : 0u, ob = bb0 ? 32u : 0u;
+    gnx_add_if_gt(oa, gnx_lds_u32(rau + gnx_feat_off(na1, lane4)), na1, 16u);
+    gnx_add_if_gt(ob, gnx_lds_u32(rbu + gnx_feat_off(nb1, lane4)), nb1, 16u);
+    const uint32_t na2 = gnx_lds_u32(rec + oa), nb2 = gnx_lds_u32(rec + ob);
+    gnx_add_if_gt(oa, gnx_lds_u32(rau + gnx_feat_off(na2, lane4)), na2, 8u);
+    gnx_add_if_gt(ob, gnx_lds_u32(rbu + gnx_feat_off(nb2, lane4)), nb2, 8u);
+    const uint32_t na3 = gnx_lds_u32(rec + 4u + oa), nb3 = gnx_lds_u32(rec + 4u + ob);
+    gnx_add_if_gt(oa, gnx_lds_u32(rau + gnx_feat_off(na3, lane4)), na3, 4u);
+    gnx_add_if_gt(ob, gnx_lds_u32(rbu + gnx_feat_off(nb3, lane4)), nb3, 4u);
+    la = gnx_lds_f32(rec + 64u + oa);
+    lb = gnx_lds_f32(rec + 64u + ob);
 }
 
 template <typename TOPT> struct TileTopLoad;
@@ -253,17 +263,18 @@ gbt_smooth_tile_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
     extern __shared__ __align__(16) unsigned char smem[];
     const int A = AT ? AT : m.A;
     constexpr int AMAX = AT ? AT : GBT_MAX_A;
-    // shared memory: [ rank tile | forest records ].  A warp always walks rows `warp` and `warp + 32` of the tile,
-    // also when the segment is shorter: such rows read past the staged slots into the forest image (valid shared
-    // memory -- the launcher checks the bound -- garbage values) and are not written.
-    uint32_t* tile = reinterpret_cast<uint32_t*>(smem);
+    // shared memory: [ forest records | rank tile ] (the records first, the tile at least GBT_TILE_FBIAS in: row bases are
+    // `tile - GBT_TILE_FBIAS`, which must not fall below the shared window).  A warp always walks rows 2 * warp and 2 * warp + 1 of the tile; when the
+    // segment is shorter those rows are clamped to its last row (valid addresses, results not written).
+    const uint32_t tile_off = max((uint32_t)forest_bytes, GBT_TILE_FBIAS);
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem + tile_off);
     {
         const uint4* src = reinterpret_cast<const uint4*>(forest_img);
-        uint4* dst = reinterpret_cast<uint4*>(smem + tile_bytes);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
         for (size_t i = threadIdx.x; i < forest_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t forest_s = tile_s + tile_bytes;
+    const uint32_t forest_s = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t tile_s = forest_s + tile_off;
     const int pad = (m.S + 1) / 2;
     const int Wp = W + m.S - 1;
     const int Lslots = Lseg + m.S - 1;
@@ -279,20 +290,28 @@ gbt_smooth_tile_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
         const int64_t n = hb * 32 + lane;
         const int w0 = sg * Lseg;
         __syncthreads();
-        // stage: the tile's slots are one contiguous run of R2; a uint4 holds 8 lanes of one element
+        // stage: the tile's slots are one contiguous run of R2; a uint4 holds 8 lanes of one element.  Tile word =
+        // rank << 17 | rank of the same class one slot on (A elements further; 0 behind the last slot of the chromosome)
         int saw_nan = 0;
         {
             const int slots = min(Lslots, Wp - w0);
             const uint4* src = reinterpret_cast<const uint4*>(R2 + ((hb * Wp + w0) * (int64_t)A) * 32);
             const int nq = slots * A * 4;
+            const int nq2 = min(Lslots + 1, Wp - w0) * A * 4;   // the slot behind the tile still belongs to this haplotype block
             for (int q = threadIdx.x; q < nq; q += blockDim.x) {
                 const uint4 v = __ldg(src + q);
+                const uint4 u = (q + 4 * A < nq2) ? __ldg(src + q + 4 * A) : make_uint4(0u, 0u, 0u, 0u);
                 uint4 lo, hi;
-                lo.x = v.x << 17; lo.y = (v.x >> 16) << 17; lo.z = v.y << 17; lo.w = (v.y >> 16) << 17;
-                hi.x = v.z << 17; hi.y = (v.z >> 16) << 17; hi.z = v.w << 17; hi.w = (v.w >> 16) << 17;
+                lo.x = (v.x << 17) | (u.x & 0xffffu); lo.y = ((v.x >> 16) << 17) | (u.x >> 16);
+                lo.z = (v.y << 17) | (u.y & 0xffffu); lo.w = ((v.y >> 16) << 17) | (u.y >> 16);
+                hi.x = (v.z << 17) | (u.z & 0xffffu); hi.y = ((v.z >> 16) << 17) | (u.z >> 16);
+                hi.z = (v.w << 17) | (u.w & 0xffffu); hi.w = ((v.w >> 16) << 17) | (u.w >> 16);
                 // NaN marker 0xFFFF in either half of any word
+                // (also in the slot behind the tile: its ranks are the low halves of the last slot's words)
                 saw_nan |= ((v.x & 0xffffu) == 0xffffu) | ((v.x >> 16) == 0xffffu) | ((v.y & 0xffffu) == 0xffffu) | ((v.y >> 16) == 0xffffu) |
-                           ((v.z & 0xffffu) == 0xffffu) | ((v.z >> 16) == 0xffffu) | ((v.w & 0xffffu) == 0xffffu) | ((v.w >> 16) == 0xffffu);
+                           ((v.z & 0xffffu) == 0xffffu) | ((v.z >> 16) == 0xffffu) | ((v.w & 0xffffu) == 0xffffu) | ((v.w >> 16) == 0xffffu) |
+                           ((u.x & 0xffffu) == 0xffffu) | ((u.x >> 16) == 0xffffu) | ((u.y & 0xffffu) == 0xffffu) | ((u.y >> 16) == 0xffffu) |
+                           ((u.z & 0xffffu) == 0xffffu) | ((u.z >> 16) == 0xffffu) | ((u.w & 0xffffu) == 0xffffu) | ((u.w >> 16) == 0xffffu);
                 uint4* dst = reinterpret_cast<uint4*>(tile + (size_t)q * 8);
                 dst[0] = lo;
                 dst[1] = hi;
@@ -302,11 +321,13 @@ gbt_smooth_tile_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
         // The walk runs in warp-uniform control flow whatever the data (uniform registers for the record and row
         // bases): rows beyond the segment / chromosome are walked and not written; a tile holding NaN is walked too
         // (harmlessly: every address is valid) and then redone by the generic traversal.
-        const int last = min(Lseg, W - w0) - 1;
-        const int wla = warp, wlb = warp + TILE_WARPS;
+        // (through a warp reduction, like `warp`: the row bases below stay in uniform registers and every feature load
+        // is [lane part + uniform row base])
+        const int last = (int)__reduce_max_sync(0xffffffffu, min(Lseg, W - w0) - 1);
+        const int wla = 2 * warp, wlb = 2 * warp + 1;
         {
-            const uint32_t rau = tile_s + (uint32_t)(wla * A * 128), rbu = tile_s + (uint32_t)(wlb * A * 128);
-            const uint32_t ral = rau + lane4, rbl = rbu + lane4;
+            const uint32_t rau = tile_s - GBT_TILE_FBIAS + (uint32_t)(min(wla, last) * A * 128);
+            const uint32_t rbu = tile_s - GBT_TILE_FBIAS + (uint32_t)(min(wlb, last) * A * 128);
             float pa[AMAX], pb[AMAX];
 #pragma unroll
             for (int c = 0; c < AMAX; c++) pa[c] = pb[c] = 0.f;
@@ -318,19 +339,21 @@ gbt_smooth_tile_kernel(const __grid_constant__ TOPT topc, GbtDev m, const unsign
                 for (int c = 0; c < AMAX; c++) {
                     if (c < A) {
                         const uint4 tp = TileTopLoad<TOPT>::get(topc, tb + c);
-                        pa[c] = GNX_FADD(pa[c], gbt_tile_tree(rau, ral, lane4, tp.x, tp.y, tp.z, tp.w, rec + c * 128));
-                        pb[c] = GNX_FADD(pb[c], gbt_tile_tree(rbu, rbl, lane4, tp.x, tp.y, tp.z, tp.w, rec + c * 128));
+                        float la, lb;
+                        gbt_tile_tree2(rau, rbu, lane4, tp.x, tp.y, tp.z, tp.w, rec + c * 128, la, lb);
+                        pa[c] = GNX_FADD(pa[c], la);
+                        pb[c] = GNX_FADD(pb[c], lb);
                     }
                 }
                 tb += A;
                 rec += 128 * A;
             }
             if (n < N && !slow) {
-                if (warp <= last) {
+                if (wla <= last) {
                     const int64_t ra = n * W + w0 + wla;
                     gbt_finish<AT>(m, pa, proba ? proba + ra * A : nullptr, label ? label + ra : nullptr);
                 }
-                if (warp + TILE_WARPS <= last) {
+                if (wlb <= last) {
                     const int64_t rb = n * W + w0 + wlb;
                     gbt_finish<AT>(m, pb, proba ? proba + rb * A : nullptr, label ? label + rb : nullptr);
                 }
@@ -365,8 +388,9 @@ int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, floa
     const int A = m->d.A, S = m->d.S;
     const size_t smem_max = 227 * 1024;
     const size_t slot_bytes = (size_t)A * 128;
-    if (m->tile_forest_bytes + 64 >= smem_max) return -1;
-    const size_t room = smem_max - m->tile_forest_bytes;
+    const size_t tile_off = std::max<size_t>(m->tile_forest_bytes, GBT_TILE_FBIAS);
+    if (tile_off + 64 >= smem_max) return -1;
+    const size_t room = smem_max - tile_off;
     const int64_t fit = (int64_t)(room / slot_bytes) - (S - 1);
     const int Lmax = (int)std::min<int64_t>(fit, 2 * TILE_WARPS);
     if (Lmax < TILE_WARPS && Lmax < W) return -1;   // a tile must give every warp a window
@@ -375,8 +399,7 @@ int gbt_tile_smooth(const gnx_gbt* m, const float* B_dev, int64_t N, int W, floa
     const int Wp = W + S - 1;
     const int64_t nhb = ceil_div(N, 32);
     const size_t tile_bytes = (size_t)(Lseg + S - 1) * slot_bytes;
-    const size_t smem = tile_bytes + m->tile_forest_bytes;
-    if ((size_t)(2 * TILE_WARPS + S - 1) * slot_bytes > smem) return -1;   // rows past the segment must stay inside shared memory
+    const size_t smem = tile_bytes + tile_off;
     // the rank scratch comes from the device's stream-ordered pool; keep freed blocks in the pool across calls
     {
         static bool pool_kept[64] = {};

@@ -83,6 +83,11 @@ constexpr int GF_CH = 5;        // (row, class) chains a thread of the re-smooth
 constexpr int GF_REC = 144;     // bytes of a tree in shared memory: block u32 [16] | leaves f32 [16] | top uint4
 
 __device__ __forceinline__ uint32_t gf_ld32(const unsigned char* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ uint32_t gf_lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
 
 // One tree for one row: the accumulating-offset walk of the row kernel (gbt_smooth.cuh: a single byte offset
 // o = 32 b0 + 16 b1 + 8 b2 + 4 b3 addresses level-2 node, level-3 node and leaf inside the tree's record) with the three top
@@ -92,13 +97,14 @@ __device__ __forceinline__ uint32_t gf_ld32(const unsigned char* p) { return *re
 __device__ __forceinline__ float gf_tree_t(const unsigned char* __restrict__ row, const unsigned char* __restrict__ rec, const uint4 t4) {
     const bool b0 = gf_ld32(row + (t4.x & 0xffffu)) > t4.x;
     const uint32_t n1 = b0 ? t4.z : t4.y;
-    uint32_t o = b0 ? 32u : 0u;
+    // the accumulating offset starts at the record's (shared) address: node and leaf loads are [o + immediate]
+    uint32_t o = (uint32_t)__cvta_generic_to_shared(rec) + (b0 ? 32u : 0u);
     gnx_add_if_gt(o, gf_ld32(row + (n1 & 0xffffu)), n1, 16u);
-    const uint32_t n2 = gf_ld32(rec + o);
+    const uint32_t n2 = gf_lds32(o);
     gnx_add_if_gt(o, gf_ld32(row + (n2 & 0xffffu)), n2, 8u);
-    const uint32_t n3 = gf_ld32(rec + 4 + o);
+    const uint32_t n3 = gf_lds32(o + 4u);
     gnx_add_if_gt(o, gf_ld32(row + (n3 & 0xffffu)), n3, 4u);
-    return *reinterpret_cast<const float*>(rec + 64 + o);
+    return __uint_as_float(gf_lds32(o + 64u));
 }
 __device__ __forceinline__ float gf_tree(const unsigned char* __restrict__ row, const unsigned char* __restrict__ rec) {
     return gf_tree_t(row, rec, *reinterpret_cast<const uint4*>(rec + 128));
