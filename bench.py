@@ -44,6 +44,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_OUT = sys.stdout   # main() re-points it at the real stdout and sends file descriptor 1 to stderr
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "chr1"
@@ -211,7 +212,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "haplotypes/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "haplotypes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -773,7 +774,7 @@ def run_ours(args):
             except Exception as e:  # a failing secondary config must not lose the headline line
                 cfgs[name] = {"error": "%s: %s" % (type(e).__name__, e)}
         out["configs"] = cfgs
-    print(json.dumps(out))
+    print(json.dumps(out), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -795,10 +796,17 @@ def main():
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer measurements")
     args = ap.parse_args()
+    # stdout carries ONE JSON line: whatever a library writes to file descriptor 1 on the way ("NCCL version ..." at
+    # communicator creation) is sent to stderr, the line itself goes to the real stdout
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    _OUT.flush()
 
 
 if __name__ == "__main__":

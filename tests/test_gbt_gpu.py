@@ -121,3 +121,32 @@ def test_gbt_ragged_trees_and_nan_default():
     got = forest.predict_proba(rows)
     want = co.gbt_rows(forest, rows)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("W,A,S,N", [(203, 7, 25, 70), (200, 3, 31, 33), (151, 7, 75, 40), (65, 5, 9, 64)])
+def test_gbt_tile_pair_words_at_segment_seams(W, A, S, N):
+    """The tile kernel's pair words (rank(slot) << 17 | rank(slot + 1)): segments of odd length (the last row pair of a
+    tile is clamped), the slot BEHIND a tile (it supplies the low half of the tile's last words) holding NaN or an exact
+    threshold hit, ranks equal to node thresholds next to large neighbours, a partial last haplotype block."""
+    from gnomix_b200 import GBTForest
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(W * 7 + S)
+    forest = GBTForest.random(rng, A, S, n_rounds=60, depth=4)
+    forest.kernel = 16
+    thr = forest.thr[forest.feat >= 0]
+    B = util.smooth_B(rng, N, W, A)
+    # half of the values sit exactly on split thresholds (rank == k: the low halves of pair and node word decide)
+    hit = rng.random(B.shape) < 0.5
+    B = np.where(hit, rng.choice(thr, size=B.shape), B).astype(np.float32)
+    # NaN around every place a segment can end, on different haplotypes
+    pad = (S + 1) // 2
+    for n in range(0, N, 3):
+        for seam in range(32, W + S, 16):
+            w = seam + (n % 7) - 3 - pad
+            if 0 <= w < W:
+                B[n, w, n % A] = np.nan
+    sm = _smoother(W, A, S, forest)
+    proba, label = sm.predict_proba(B), sm.predict(B)
+    p_o, l_o = co.gbt_smooth(forest, B, S)
+    assert np.array_equal(proba.view(np.uint32), p_o.view(np.uint32))
+    assert np.array_equal(label, l_o)
