@@ -454,7 +454,13 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
             LAUNCHR(AT, 0, GbtTopC, none);                         \
         }                                                          \
     } while (0)
-            GBT_DISPATCH_A(m->d.A, CALLR)
+            // the accumulating-offset walk (the production row kernel) is specialised per A; the first image's walk
+            // (forests with more trees than the parameter bank holds, cross-checks) runs the generic-A instantiation
+            if (var == 4) {
+                GBT_DISPATCH_A(m->d.A, CALLR)
+            } else {
+                CALLR(0);
+            }
 #undef CALLR
 #undef LAUNCHR
             GNX_CUDA(cudaGetLastError());
@@ -475,7 +481,7 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
             gbt_smooth_kernel<AT, false><<<grid, 512, smem, st>>>(m->d, m->forest_bytes, B_dev, N, W, proba_dev, label_dev);     \
         }                                                                                                          \
     } while (0)
-    GBT_DISPATCH_A(m->d.A, CALL)
+    CALL(0);   // generic float traversal (forests deeper than 4 levels, cross-checks): one generic-A instantiation
 #undef CALL
     GNX_CUDA(cudaGetLastError());
     return 0;

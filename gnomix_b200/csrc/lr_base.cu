@@ -101,22 +101,41 @@ int lr_launch_dp4a_any(const gnx_lr* m, const int8_t* X, int64_t N, int64_t ldX,
     return f64 ? lr_launch_dp4a<double>(m, X, N, ldX, (double*)B, st) : lr_launch_dp4a<float>(m, X, N, ldX, (float*)B, st);
 }
 
+// split model (A > 8): row-normalise the un-normalised sigmoids of the two class groups (sklearn _predict_proba_lr:
+// p /= p.sum(axis=1), numpy's summation order) into B [rows, na0 + na1]
+template <typename OutT>
+__global__ void lr_split_normalise_kernel(const double* __restrict__ p0, const double* __restrict__ p1, int na0, int na1, int64_t rows,
+                                          OutT* __restrict__ B) {
+    const int A = na0 + na1;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        double p[16];
+#pragma unroll
+        for (int a = 0; a < 16; a++) p[a] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+            if (a < na0) p[a] = p0[r * na0 + a];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+            if (a < na1) p[8 + a] = p1[r * na1 + a];
+        const double s = lr_np_sum<16>(p, A);
+#pragma unroll
+        for (int a = 0; a < 16; a++)
+            if (a < A) B[r * A + a] = lr_out<OutT>(GNX_DIV(p[a], s));
+    }
+}
+
 }  // namespace gnx
 
 using namespace gnx;
 
 extern "C" {
 
-int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx, const double* coef,
-                        const double* intercept, int limbs) {
-    GNX_REQUIRE(out != nullptr, "gnx_lr_model_create: out is NULL");
-    *out = nullptr;
-    GNX_REQUIRE(A >= 2 && A <= 16, "gnx_lr_model_create: A=%d unsupported (2..16)", A);
-    GNX_REQUIRE(C > 0 && M > 0 && M <= C && ctx >= 0 && ctx <= C, "gnx_lr_model_create: bad geometry C=%lld M=%lld ctx=%lld",
-                (long long)C, (long long)M, (long long)ctx);
-    GNX_REQUIRE(coef && intercept, "gnx_lr_model_create: NULL weights");
-    if (require_blackwell()) return 1;
-    const int Ar = (A == 2) ? 1 : A;
+// One packed model.  A = classes of the output row (its stride), Ar = coefficient rows per window (1 for the binary layout),
+// raw = 1 for a class group of a split model (un-normalised float64 sigmoids out), s_forced >= 0 fixes the fixed-point
+// exponent (the class groups of a split model share the exponent chosen over ALL classes, so every logit is the one a
+// single 7-limb model would produce).
+static int lr_create_one(gnx_lr_t** out, int A, int Ar, int raw, int s_forced, int64_t C, int64_t M, int64_t ctx, const double* coef,
+                         const double* intercept, int limbs, int* s_chosen) {
     const int apad = (Ar <= 8) ? 8 : 16;
     const int Lmax = LR_NCOLS / apad;
     int L = limbs == 0 ? 7 : limbs;
@@ -167,10 +186,14 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
         frexp(ssum, &e2);
         s = std::min(8 * L - 2 - e1, 60 - e2);
     }
+    if (s_forced >= 0) s = s_forced;
     GNX_REQUIRE(s >= 8 && s <= 1000, "gnx_lr_model_create: weights out of range for fixed point (s=%d)", s);
+    if (s_chosen) *s_chosen = s;
+    if (out == nullptr) return 0;   // scale selection only
     const double scale = ldexp(1.0, s);
 
     gnx_lr* m = new gnx_lr();
+    m->sub[0] = m->sub[1] = nullptr;
     m->kernel_sel = 0;
     m->tmap_w_ready = false;
     m->d_blob = nullptr;
@@ -264,7 +287,7 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
     }
     LrDev& d = m->d;
     d.A = A; d.Ar = Ar; d.L = L; d.apad = apad; d.s = s; d.W = (int)W;
-    d.C = C; d.M = M; d.ctx = ctx; d.n_chunks = n_chunks; d.dbg = 0;
+    d.C = C; d.M = M; d.ctx = ctx; d.n_chunks = n_chunks; d.dbg = 0; d.raw = raw;
     d.wt = reinterpret_cast<const int8_t*>(blob + o_tiles);
     d.bias = reinterpret_cast<const double*>(blob + o_bias);
     d.k0 = reinterpret_cast<const int32_t*>(blob + o_k0);
@@ -277,8 +300,94 @@ int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx
     return 0;
 }
 
+int gnx_lr_model_create(gnx_lr_t** out, int A, int64_t C, int64_t M, int64_t ctx, const double* coef,
+                        const double* intercept, int limbs) {
+    GNX_REQUIRE(out != nullptr, "gnx_lr_model_create: out is NULL");
+    *out = nullptr;
+    GNX_REQUIRE(A >= 2 && A <= 16, "gnx_lr_model_create: A=%d unsupported (2..16)", A);
+    GNX_REQUIRE(C > 0 && M > 0 && M <= C && ctx >= 0 && ctx <= C, "gnx_lr_model_create: bad geometry C=%lld M=%lld ctx=%lld",
+                (long long)C, (long long)M, (long long)ctx);
+    GNX_REQUIRE(coef && intercept, "gnx_lr_model_create: NULL weights");
+    if (require_blackwell()) return 1;
+    const int Ar = (A == 2) ? 1 : A;
+    const int L = limbs == 0 ? 7 : limbs;
+    if (Ar <= 8 || L <= LR_NCOLS / 16) return lr_create_one(out, A, Ar, 0, -1, C, M, ctx, coef, intercept, limbs, nullptr);
+    // A > 8 with more than 4 limbs: 16-column limb groups leave room for 4 limbs in the 64 accumulator columns of a
+    // window, so the classes are split into two groups of <= 8, each packed with the full limb count under ONE
+    // exponent, run one after the other and normalised together (lr_split_normalise_kernel)
+    int s = 0;
+    {
+        // exponent over all classes for L limbs: the selection pass of a 16-column model with its limb clamp lifted
+        const int64_t W = C / M, rem = C - M * W, M_ = M + 2 * ctx;
+        double amax = 0.0, ssum = 0.0;
+        std::vector<double> f;
+        int64_t off = 0;
+        for (int64_t w = 0; w < W; w++) {
+            const int64_t lo = (w == W - 1) ? (C + 2 * ctx - (M_ + rem)) : w * M, len = (w == W - 1) ? (M_ + rem) : M_;
+            const int64_t s0 = std::max<int64_t>(0, w * M - ctx), e0 = (w == W - 1) ? C : std::min<int64_t>(C, w * M + M + ctx);
+            f.assign((size_t)(e0 - s0), 0.0);
+            for (int a = 0; a < Ar; a++) {
+                std::fill(f.begin(), f.end(), 0.0);
+                const double* cf = coef + off + (int64_t)a * len;
+                for (int64_t j = 0; j < len; j++) {
+                    GNX_REQUIRE(std::isfinite(cf[j]), "gnx_lr_model_create: non-finite coefficient (window %lld)", (long long)w);
+                    f[pad_to_orig(lo + j, C, ctx) - s0] += cf[j];
+                }
+                double sa = 0.0;
+                for (double v : f) {
+                    amax = std::max(amax, fabs(v));
+                    sa += fabs(v);
+                }
+                ssum = std::max(ssum, sa);
+            }
+            off += (int64_t)Ar * len;
+        }
+        if (amax == 0.0) {
+            s = 8 * L - 2;
+        } else {
+            int e1, e2;
+            frexp(amax, &e1);
+            frexp(ssum, &e2);
+            s = std::min(8 * L - 2 - e1, 60 - e2);
+        }
+        GNX_REQUIRE(s >= 8 && s <= 1000, "gnx_lr_model_create: weights out of range for fixed point (s=%d)", s);
+    }
+    gnx_lr* m = new gnx_lr();
+    m->sub[0] = m->sub[1] = nullptr;
+    m->kernel_sel = 0;
+    m->tmap_w_ready = false;
+    m->d_blob = nullptr;
+    m->n_tiles = 0;
+    cudaGetDevice(&m->device);
+    m->d = LrDev{};
+    m->d.A = A; m->d.Ar = Ar; m->d.L = L; m->d.apad = 16; m->d.s = s; m->d.W = (int)(C / M);
+    m->d.C = C; m->d.M = M; m->d.ctx = ctx;
+    const int64_t W = C / M, rem = C - M * W, M_ = M + 2 * ctx;
+    const int grp[3] = {0, 8, Ar};
+    for (int g = 0; g < 2; g++) {
+        const int a0 = grp[g], na = grp[g + 1] - grp[g];
+        std::vector<double> cs, is((size_t)W * na);
+        int64_t off = 0;
+        for (int64_t w = 0; w < W; w++) {
+            const int64_t len = (w == W - 1) ? (M_ + rem) : M_;
+            cs.insert(cs.end(), coef + off + (int64_t)a0 * len, coef + off + (int64_t)(a0 + na) * len);
+            for (int a = 0; a < na; a++) is[(size_t)w * na + a] = intercept[(size_t)w * Ar + a0 + a];
+            off += (int64_t)Ar * len;
+        }
+        const int rc = lr_create_one(&m->sub[g], na, na, 1, s, C, M, ctx, cs.data(), is.data(), L, nullptr);
+        if (rc) {
+            gnx_lr_model_destroy(m);
+            return rc;
+        }
+    }
+    *out = m;
+    return 0;
+}
+
 void gnx_lr_model_destroy(gnx_lr_t* m) {
     if (!m) return;
+    for (int g = 0; g < 2; g++)
+        if (m->sub[g]) gnx_lr_model_destroy(m->sub[g]);
     if (m->d_blob) cudaFree(m->d_blob);
     delete m;
 }
@@ -290,6 +399,8 @@ int gnx_lr_set_kernel(gnx_lr_t* m, int which) {
     GNX_REQUIRE(m != nullptr, "gnx_lr_set_kernel: NULL model");
     GNX_REQUIRE(which == 0 || which == 1, "gnx_lr_set_kernel: unknown kernel %d", which);
     m->kernel_sel = which;
+    for (int g = 0; g < 2; g++)
+        if (m->sub[g]) m->sub[g]->kernel_sel = which;
     return 0;
 }
 
@@ -300,6 +411,27 @@ static int lr_predict_any(const gnx_lr_t* m, const int8_t* X, int64_t N, int64_t
     GNX_REQUIRE(X && B, "gnx_lr_predict: NULL buffer");
     GNX_REQUIRE(ceil_div(N, 128) <= 65535, "gnx_lr_predict: N too large for one call (%lld)", (long long)N);
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->sub[0]) {
+        // split model (A > 8): the two class groups write expit(d) as float64 [N, W, 8] / [N, W, A - 8]; one pass
+        // normalises the A values of a row in numpy's summation order
+        const int A = m->d.A, na0 = m->sub[0]->d.A, na1 = m->sub[1]->d.A;
+        const int64_t rows = N * m->d.W;
+        double* p0 = nullptr;
+        GNX_CUDA(cudaMallocAsync((void**)&p0, sizeof(double) * (size_t)rows * (na0 + na1), st));
+        double* p1 = p0 + (size_t)rows * na0;
+        int rc = lr_predict_any(m->sub[0], X, N, ldX, p0, true, stream);
+        if (!rc) rc = lr_predict_any(m->sub[1], X, N, ldX, p1, true, stream);
+        if (!rc) {
+            const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 256), (int64_t)sm_count() * 16);
+            if (f64) lr_split_normalise_kernel<double><<<grid, 256, 0, st>>>(p0, p1, na0, na1, rows, (double*)B);
+            else lr_split_normalise_kernel<float><<<grid, 256, 0, st>>>(p0, p1, na0, na1, rows, (float*)B);
+            if (cudaGetLastError() != cudaSuccess) rc = 1;
+            (void)A;
+        }
+        cudaFreeAsync(p0, st);
+        if (rc == 1 && !gnx_last_error()[0]) set_error("gnx_lr_predict: split-model launch failed");
+        return rc;
+    }
     if (m->kernel_sel == 0) return lr_launch_tc(m, X, N, ldX, B, f64, st);
     return lr_launch_dp4a_any(m, X, N, ldX, B, f64, st);
 }

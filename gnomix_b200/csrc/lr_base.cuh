@@ -16,6 +16,7 @@ struct LrDev {
     int A, Ar, L, apad, s, W;
     int64_t C, M, ctx;
     int n_chunks;
+    int raw;                   // 1: a class group of a split model (A > 8): store expit(d) as float64, stride A, no normalisation
     int dbg;                   // profiling switches (GNX_LR_DBG): 1 = no MMA, 2 = no MMA + no epilogue math, 4 = no weight loads
     const int8_t* wt;          // [n_tiles][LR_NCOLS][LR_KC] int8 limb planes; column = limb*apad + class
     const double* bias;        // [W][Ar]
@@ -40,6 +41,10 @@ struct gnx_lr {
     // TMA descriptor of the weight tensor (128 bytes, CUtensorMap) -- built lazily
     alignas(64) unsigned char tmap_w[128];
     bool tmap_w_ready;
+    // A > 8 with the full 7 limbs: two class groups of <= 8 classes (each a model of its own, `raw` output, the SAME
+    // fixed-point scale), run one after the other and normalised together (lr_base.cu); this handle then only carries
+    // the geometry in `d`
+    gnx_lr* sub[2];
 };
 
 namespace gnx {
@@ -53,6 +58,34 @@ template <>
 __device__ __forceinline__ double lr_out<double>(double v) { return v; }
 template <>
 __device__ __forceinline__ float lr_out<float>(double v) { return GNX_D2F(v); }
+
+// numpy add.reduce order over the A class probabilities of a row (gnx_np_sum): sequential below 8 terms, 8-lane
+// pairwise from 8 on
+template <int APAD>
+__device__ __forceinline__ double lr_np_sum(const double (&p)[APAD], int A) {
+    double s;
+    if (A < 8) {
+        s = 0.0;
+#pragma unroll
+        for (int a = 0; a < (APAD < 8 ? APAD : 8); a++)
+            if (a < A) s = GNX_ADD(s, p[a]);
+    } else {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = p[j];
+        if (APAD > 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (A >= 16) r[j] = GNX_ADD(r[j], p[(8 + j) % APAD]);
+        }
+        s = GNX_ADD(GNX_ADD(GNX_ADD(r[0], r[1]), GNX_ADD(r[2], r[3])), GNX_ADD(GNX_ADD(r[4], r[5]), GNX_ADD(r[6], r[7])));
+        const int done = (A >= 16) ? 16 : 8;
+#pragma unroll
+        for (int a = 8; a < APAD; a++)
+            if (a >= done && a < A) s = GNX_ADD(s, p[a]);
+    }
+    return s;
+}
 
 // (hap, window) epilogue shared by both kernels: limb recombination (exact int64),
 // scale, intercept, expit, row-normalise (sklearn _predict_proba_lr), store.
@@ -75,6 +108,12 @@ __device__ __forceinline__ void lr_epilogue_store(const int32_t (&acc)[LR_NCOLS]
         d[a] = 0.0;
         if (a < m.Ar) d[a] = GNX_ADD(GNX_MUL(GNX_LL2D(tot), scale), __ldg(m.bias + (int64_t)w * m.Ar + a));
     }
+    if (m.raw) {   // class group of a split model: un-normalised sigmoids, float64 (OutT is double on this path)
+#pragma unroll
+        for (int a = 0; a < APAD; a++)
+            if (a < m.Ar) out[a] = lr_out<OutT>(gnx_expit(d[a]));
+        return;
+    }
     if (m.A == 2) {
         double p = gnx_expit(d[0]);
         out[0] = lr_out<OutT>(GNX_SUB(1.0, p));
@@ -84,28 +123,7 @@ __device__ __forceinline__ void lr_epilogue_store(const int32_t (&acc)[LR_NCOLS]
     double p[APAD];
 #pragma unroll
     for (int a = 0; a < APAD; a++) p[a] = (a < m.A) ? gnx_expit(d[a]) : 0.0;
-    // numpy add.reduce order (gnx_np_sum): sequential below 8 terms, 8-lane pairwise from 8 on
-    double s;
-    if (m.A < 8) {
-        s = 0.0;
-#pragma unroll
-        for (int a = 0; a < (APAD < 8 ? APAD : 8); a++)
-            if (a < m.A) s = GNX_ADD(s, p[a]);
-    } else {
-        double r[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) r[j] = p[j];
-        if (APAD > 8) {
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (m.A >= 16) r[j] = GNX_ADD(r[j], p[(8 + j) % APAD]);
-        }
-        s = GNX_ADD(GNX_ADD(GNX_ADD(r[0], r[1]), GNX_ADD(r[2], r[3])), GNX_ADD(GNX_ADD(r[4], r[5]), GNX_ADD(r[6], r[7])));
-        const int done = (m.A >= 16) ? 16 : 8;
-#pragma unroll
-        for (int a = 8; a < APAD; a++)
-            if (a >= done && a < m.A) s = GNX_ADD(s, p[a]);
-    }
+    const double s = lr_np_sum<APAD>(p, m.A);
 #pragma unroll
     for (int a = 0; a < APAD; a++)
         if (a < m.A) out[a] = lr_out<OutT>(GNX_DIV(p[a], s));

@@ -58,8 +58,11 @@ int gnx_selftest_math(int64_t n, uint64_t seed, int64_t* mismatches);
  *            reference's padded window (reflect pad included), A_rows = A (A > 2)
  *            or 1 (A == 2, sklearn binary layout).
  * intercept: [W, A_rows] float64.
- * limbs:     signed base-256 digits per fixed-point weight (0 = default 7; A > 8 uses
- *            16-column limb groups and at most 4 limbs).  Windows up to 131000 SNPs.  The
+ * limbs:     signed base-256 digits per fixed-point weight (0 = default 7).  A > 8 with more
+ *            than 4 limbs is packed as two class groups of <= 8 under one exponent, run one
+ *            after the other (X is read twice) and normalised together -- the same exact
+ *            logits as for A <= 8; limbs <= 4 keeps the single-pass 16-column model
+ *            (|logit error| ~1e-6).  Windows up to 131000 SNPs.  The
  *            fixed-point scale is chosen so that the int64 totals cannot overflow for
  *            |x| <= 2 (the reference's matrix only holds {0,1,2}).
  * Environment GNX_LR_DBG (bit mask, profiling only): 1 skip MMAs, 2 skip the

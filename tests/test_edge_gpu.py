@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
     (1100, 500, 4, 130, 0.5),     # W = 2
     (9000, 4200, 7, 1, 0.5),      # single haplotype, windows of 8400+ SNPs
     (6000, 500, 8, 70, 0.5),      # A = 8: a full 8-column limb group
-    (6000, 500, 9, 70, 0.5),      # A = 9: 16-column groups, 4 limbs
+    (6000, 500, 9, 70, 0.5),      # A = 9: split model (8 + 1 classes), 7 limbs
     (5000, 400, 16, 33, 0.5),     # A = 16
     (8000, 640, 7, 200, 0.25),    # context ratio 0.25
     (8000, 640, 7, 200, 1.0),     # context as wide as the window (5 windows live per chunk -> dp4a path)
@@ -27,7 +27,7 @@ def test_lr_edge_geometries(C, M, A, N, ctx_ratio):
     coefs, icpts, ctx = util.random_lr(rng, C, M, A, ctx_ratio=ctx_ratio)
     X = util.random_haplotypes(rng, N, C)
     base = util.make_lr_base(C, M, A, coefs, icpts, ctx_ratio=ctx_ratio)
-    limbs = 7 if A <= 8 else 4
+    limbs = 7
     (Bf_o, Bd_o), s = util.oracle_lr_fixed(X, coefs, icpts, C, M, ctx, A, limbs=limbs, want_f64=True)
     Xd = torch.from_numpy(X).cuda()
     for kernel in (0, 1):
@@ -35,7 +35,7 @@ def test_lr_edge_geometries(C, M, A, N, ctx_ratio):
         Bf = base.predict_proba(Xd).cpu().numpy()
         assert np.array_equal(Bf.view(np.uint32), Bf_o.view(np.uint32)), "kernel %d" % kernel
     B64 = co.lr_f64(X, coefs, np.stack(icpts), C, M, ctx, A)
-    assert np.max(np.abs(Bd_o - B64)) < (1e-12 if limbs == 7 else 1e-5)
+    assert np.max(np.abs(Bd_o - B64)) < 1e-12
     Bh = base.predict_proba(X)                       # numpy in -> float64 out
     assert Bh.dtype == np.float64 and np.array_equal(Bh.view(np.uint64), Bd_o.view(np.uint64))
 

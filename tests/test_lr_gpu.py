@@ -14,7 +14,9 @@ CASES = [
     (4099, 256, 3, 64),       # ctx=128 == one chunk
     (20011, 857, 7, 513),     # demo-like window size, N = 2 tiles + 1
     (9000, 1000, 2, 100),     # binary layout [1-p, p]
-    (3001, 200, 12, 130),     # A > 8 -> 16-wide limb groups
+    (3001, 200, 12, 130),     # A > 8 -> split model: two class groups of <= 8, 7 limbs each, one exponent
+    (2900, 180, 16, 70),      # A = 16: two full groups (numpy's 8-lane pairwise sum over 16 terms)
+    (2900, 180, 9, 70),       # A = 9: a group of one class
     (2500, 100, 5, 257),      # windows narrower than a chunk (dp4a fallback inside tc path)
 ]
 
@@ -29,7 +31,7 @@ def test_lr_matches_oracle(C, M, A, N, kernel):
     X = util.random_haplotypes(rng, N, C)
     base = util.make_lr_base(C, M, A, coefs, icpts)
     base.kernel = kernel
-    limbs = 7 if A <= 8 else 4
+    limbs = 7
     (Bf_o, Bd_o), s = util.oracle_lr_fixed(X, coefs, icpts, C, M, ctx, A, limbs=limbs, want_f64=True)
     assert base.fixed_point_scale() == s
     Xd = torch.from_numpy(X).cuda()
@@ -40,8 +42,7 @@ def test_lr_matches_oracle(C, M, A, N, kernel):
     assert np.array_equal(Bd.view(np.uint64), Bd_o.view(np.uint64)), "float64 B not bit-exact vs fixed-point oracle"
     # and the fixed-point path agrees with the float64 restatement of sklearn
     B64 = co.lr_f64(X, coefs, np.stack(icpts), C, M, ctx, A)
-    tol = 1e-12 if limbs == 7 else 1e-5
-    assert np.max(np.abs(Bd - B64)) < tol
+    assert np.max(np.abs(Bd - B64)) < 1e-12
 
 
 def test_lr_numpy_in_numpy_out():
@@ -100,3 +101,25 @@ def test_lr_against_reference_golden(name, kernel):
     # the numpy-in / numpy-out plugin call returns the reference's dtype and values
     B_np = base.predict_proba(X)
     assert B_np.dtype == np.float64 and np.max(np.abs(B_np - B_ref)) < 1e-12
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_lr_wide_model_with_four_limbs_stays_selectable(kernel):
+    """A > 8 with limbs=4 asked for explicitly: the single-pass 16-column model (one read of X, |logit error| ~1e-6) --
+    bit-exact against the fixed-point oracle at ITS exponent, 1e-5 from the float64 path."""
+    import torch
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(5)
+    C, M, A, N = 3001, 200, 12, 40
+    coefs, icpts, ctx = util.random_lr(rng, C, M, A)
+    X = util.random_haplotypes(rng, N, C)
+    base = util.make_lr_base(C, M, A, coefs, icpts)
+    base.kernel = kernel
+    base.limbs = 4
+    (Bf_o, Bd_o), s = util.oracle_lr_fixed(X, coefs, icpts, C, M, ctx, A, limbs=4, want_f64=True)
+    assert base.fixed_point_scale() == s
+    Xd = torch.from_numpy(X).cuda()
+    assert np.array_equal(base.predict_proba(Xd).cpu().numpy().view(np.uint32), Bf_o.view(np.uint32))
+    Bd = base.predict_proba_f64(Xd).cpu().numpy()
+    assert np.array_equal(Bd.view(np.uint64), Bd_o.view(np.uint64))
+    assert np.max(np.abs(Bd - co.lr_f64(X, coefs, np.stack(icpts), C, M, ctx, A))) < 1e-5
