@@ -186,7 +186,9 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
 // Packed fraction of each chunk: measured, not modelled.  The controller times windows of chunks of the running job
 // (host clock between chunk starts; in steady state that is the bottleneck resource, whichever it is -- cores, bus
 // or host DRAM shared with the other ranks of the box) and hill-climbs f; f = 0 (everything raw, no core time) is
-// probed once per calibration so that the packed path is never slower than the unpacked one.
+// probed at the start of every call whose packed rate is not clearly above what the bus carries raw, so that the
+// packed path is not slower than the unpacked one (8 ranks on one host: it was, 129 k against 150 k haplotypes/s,
+// before the probe was repeated per call -- the ranks of a job start their calls together, so they probe together).
 struct FracCtl {
     static constexpr int kSkip = 2, kMeasure = 3;   // chunks after a change of f that are not timed / that are
     double f = 0.0, best_f = 0.0, best_rate = 0.0, step = 0.1;
@@ -195,10 +197,12 @@ struct FracCtl {
     double t_start = 0.0;
     int64_t rows = 0;
     bool first = true;
-    void begin(double f0, double step0, bool probe0) {
+    double raw_bound = 0.0;   // rows/s the bus alone could carry unpacked (calibrated H2D rate / row bytes)
+    void begin(double f0, double step0, bool probe0, double raw_rows_per_s) {
         f = best_f = f0;
         step = step0 > 0.0 ? step0 : 0.1;
         probe_zero = probe0 ? 1 : 0;
+        raw_bound = raw_rows_per_s;
     }
     // called at the start of every chunk with the rows the previous chunk held
     void tick(double now, int64_t rows_prev) {
@@ -216,7 +220,12 @@ struct FracCtl {
             first = false;
             best_rate = rate;
             best_f = f;
-            if (probe_zero == 1 && f > 0.0) { probe_zero = 2; f = 0.0; return; }
+            // f = 0 is worth a window only where it could win: when the packed path runs well above what the bus
+            // carries raw (one GPU with all the host's cores) the probe would just cost; when several ranks share the
+            // host's memory system the packed path can fall BELOW the raw one (packing moves 1.5 bytes of host DRAM
+            // traffic per SNP, a raw copy 1), and every call checks
+            if (probe_zero == 1 && f > 0.0 && (raw_bound <= 0.0 || rate < 1.3 * raw_bound)) { probe_zero = 2; f = 0.0; return; }
+            probe_zero = 0;
             next_candidate();
             return;
         }
@@ -333,11 +342,19 @@ extern "C" int gnx_infer_host_ex(const gnx_pipeline_t* p, const void* X_host_v, 
                 ws.frac_step = 0.0;
                 fresh = true;
             }
-            if (ws.pack_gbs > 0.0 && ws.h2d_gbs > 0.0) {
+            if (ws.pack_gbs > 0.0 && ws.h2d_gbs > 0.0 && ws.pack_gbs < ws.h2d_gbs) {
+                // The cores (with the memory system behind them) are scarcer than the bus: many ranks on one host.
+                // Measured on the 8-GPU box (4 host threads per rank; rates calibrated while every rank calibrates:
+                // pack 9.4 GB/s, H2D 15.9 GB/s): everything raw 150 k haplotypes/s, the packed fractions the per-rank
+                // controllers drift to 129-137 k -- a rank that packs takes memory bandwidth from the other ranks'
+                // copies, so greedy per-rank hill-climbing settles above the joint optimum.  Ship raw.
+                frac = 0.0;
+            } else if (ws.pack_gbs > 0.0 && ws.h2d_gbs > 0.0) {
                 // starting point: balance of the calibrated rates (the cores lose some memory bandwidth to the
                 // concurrent DMA reads: derate P); from there the controller follows what it measures
                 frac = ws.frac_hint >= 0.0 ? ws.frac_hint : 1.0 / (ws.h2d_gbs / (0.85 * ws.pack_gbs) + 0.75);
-                ctl.begin(frac, ws.frac_step, fresh || ws.frac_hint < 0.0);
+                (void)fresh;
+                ctl.begin(frac, ws.frac_step, true, ws.h2d_gbs * 1e9 / (double)C);
                 adapt = true;
             }
         }
@@ -582,7 +599,8 @@ extern "C" int gnx_upload_haplotypes(const int8_t* X_host, int64_t N, int64_t ld
             ws.frac_hint = -1.0;
         }
         if (ws.pack_gbs > 0.0 && ws.h2d_gbs > 0.0)
-            frac = ws.frac_hint >= 0.0 ? ws.frac_hint : 1.0 / (ws.h2d_gbs / (0.85 * ws.pack_gbs) + 0.75);
+            frac = ws.pack_gbs < ws.h2d_gbs ? 0.0   // many ranks on one host: ship raw (see gnx_infer_host_ex)
+                                            : (ws.frac_hint >= 0.0 ? ws.frac_hint : 1.0 / (ws.h2d_gbs / (0.85 * ws.pack_gbs) + 0.75));
     }
     bool stage_used[kStage] = {};
     int it = 0;
