@@ -110,3 +110,30 @@ def test_upload_haplotypes_equals_plain_copy(libgnx, monkeypatch):
         assert np.array_equal(Yd.cpu().numpy(), Y)
         monkeypatch.delenv("GNX_HOST_PACK")
         assert libgnx.gnx_release_workspace() == 0          # buffers come back on demand
+
+
+def test_infer_host_ships_raw_when_the_cores_are_scarcer_than_the_bus(monkeypatch):
+    """One host thread packs slower than the bus copies (the situation of many ranks sharing one host): the pipeline
+    must then ship every row raw instead of packing a fraction (a packing rank takes memory bandwidth from the other
+    ranks' copies) -- same labels, packed fraction 0."""
+    import torch
+    from gnomix_b200 import _lib
+    C_, M, A, S, N = 400_013, 2000, 7, 15, 768
+    model, rng = _model(C_, M, A, S, 5)
+    X = util.random_haplotypes(rng, N, C_)
+    Xh = torch.from_numpy(X).pin_memory()
+    monkeypatch.setenv("GNX_HOST_PACK", "0")
+    ref = model.predict_host(Xh, chunk_haps=256)
+    monkeypatch.delenv("GNX_HOST_PACK")
+    monkeypatch.setenv("GNX_HOST_THREADS", "1")
+    _lib.check(_lib.lib().gnx_release_workspace())          # forget the calibration of earlier tests
+    got = model.predict_host(Xh, chunk_haps=256)
+    pk, h2d = C.c_double(0), C.c_double(0)
+    _lib.lib().gnx_infer_host_rates(C.byref(pk), C.byref(h2d))
+    frac, a, b = C.c_double(-1), C.c_int64(0), C.c_int64(0)
+    _lib.lib().gnx_infer_host_last_transfer(C.byref(frac), C.byref(a), C.byref(b))
+    monkeypatch.delenv("GNX_HOST_THREADS")
+    _lib.check(_lib.lib().gnx_release_workspace())
+    assert np.array_equal(got, ref)
+    assert 0 < pk.value < h2d.value, (pk.value, h2d.value)   # one thread: ~8 GB/s against ~50 GB/s
+    assert frac.value == 0.0
