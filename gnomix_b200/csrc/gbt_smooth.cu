@@ -445,21 +445,14 @@ int gnx_gbt_smooth(const gnx_gbt_t* m, const float* B_dev, int64_t N, int W, flo
         gbt_smooth_rank_kernel<AT, VAR, TOPT><<<grid, RK_THREADS, smem, st>>>(TOPV, m->d, img, img_bytes, B_dev, N, W, bestG, bestL, \
                                                                               proba_dev, label_dev);                           \
     } while (0)
-#define CALLR(AT)                                                  \
-    do {                                                           \
-        if (var == 4) {                                            \
-            LAUNCHR(AT, 4, GbtTopC, *m->h_topc);                   \
-        } else {                                                   \
-            static const GbtTopC none{};                           \
-            LAUNCHR(AT, 0, GbtTopC, none);                         \
-        }                                                          \
-    } while (0)
+#define CALLR(AT) LAUNCHR(AT, 4, GbtTopC, *m->h_topc)
             // the accumulating-offset walk (the production row kernel) is specialised per A; the first image's walk
             // (forests with more trees than the parameter bank holds, cross-checks) runs the generic-A instantiation
             if (var == 4) {
                 GBT_DISPATCH_A(m->d.A, CALLR)
             } else {
-                CALLR(0);
+                static const GbtTopC none{};
+                LAUNCHR(0, 0, GbtTopC, none);
             }
 #undef CALLR
 #undef LAUNCHR
