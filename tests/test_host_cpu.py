@@ -272,3 +272,23 @@ def test_xgboost_json_roundtrip_and_exported_model(tmp_path):
     c2, b2 = m.base.packed_weights()
     assert np.array_equal(c2, np.concatenate([c.ravel() for c in coefs])) and np.array_equal(b2, np.stack(icpts))
     assert list(m.gen_map_df["pos"]) == [1, 40000]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference runs without a GPU (the CPU port of the reference path) and prints exactly ONE JSON
+    line on stdout carrying the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-haps", "8"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "haplotypes/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "haplotypes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["data"] == "synthetic"
