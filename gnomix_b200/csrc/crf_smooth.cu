@@ -231,7 +231,8 @@ crf_smooth_lanes_kernel(CrfDev m, const double* __restrict__ B, int64_t N, int W
     for (int t0 = last0; t0 >= 0; t0 -= CRF_TB) {
         const int nt = min(CRF_TB, W - t0);
         for (int i = y; i < nt * A; i += 8) sb[i] = __ldg(b + (int64_t)t0 * A + i);
-        for (int i = y; i < nt * L; i += 8) so[i] = out[(int64_t)t0 * L + i];
+        // (idle groups shadow the last haplotype: they do not read rows its own group may still be writing)
+        for (int i = y; i < nt * L; i += 8) so[i] = live ? out[(int64_t)t0 * L + i] : 1.0;
         __syncwarp();
         for (int tt = nt - 1; tt >= 0; tt--) {
             const int t = t0 + tt;
