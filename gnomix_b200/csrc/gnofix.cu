@@ -60,6 +60,7 @@ struct GfArgs {
     const uint32_t* diff;    // [n][nw] bit j: original haplotypes differ in SNP block j
     uint32_t* trk_out;       // [n][nw] final tracker bits
     uint32_t* hist;          // [grid * teams][max_it][nw] tracker history of the individual a team is working on
+    const int* nanflag;      // [n] the individual's base probabilities hold a NaN: refused (labels -1, pair left as it is)
     int32_t* Y;              // [2n][W] in: smoother labels of the original pair; out: final labels
     int32_t* tracker;        // [2n][W] or NULL
     int* counter;            // work queue
@@ -189,6 +190,18 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ block_img, const uint4
         team_sync(team);
         const int64_t ind = ctl[0];
         if (ind >= g.n_ind) break;
+        if (g.nanflag[ind]) {
+            // NaN among the pair's base probabilities: the smoother kernels follow each node's default child, the rank
+            // form of this kernel cannot (a NaN has no rank) -- refuse loudly instead of phasing with other semantics
+            for (int i = tid; i < 2 * W; i += GF_TEAM) g.Y[(size_t)(2 * ind) * W + i] = -1;
+            for (int i = tid; i < nw; i += GF_TEAM) g.trk_out[(size_t)ind * nw + i] = 0u;
+            if (g.tracker)
+                for (int i = tid; i < W; i += GF_TEAM) {
+                    g.tracker[(size_t)(2 * ind) * W + i] = 0;
+                    g.tracker[(size_t)(2 * ind + 1) * W + i] = 1;
+                }
+            continue;
+        }
         const uint16_t* rk0 = g.ranks + (size_t)(2 * ind) * W * A;   // original haplotype 0; haplotype 1 follows
         for (int i = tid; i < 2 * W; i += GF_TEAM) Ys[i] = (signed char)g.Y[(size_t)(2 * ind) * W + i];
         for (int i = tid; i < nw; i += GF_TEAM) {
@@ -418,9 +431,11 @@ gnofix_kernel(GbtDev m, const unsigned char* __restrict__ block_img, const uint4
 
 // rank of every original base probability (exact, see gbt_smooth.cuh); NaN ranks above
 // every threshold.
-__global__ void gnofix_rank_kernel(GbtDev m, const float* __restrict__ B, int64_t count, uint16_t* __restrict__ out) {
+__global__ void gnofix_rank_kernel(GbtDev m, const float* __restrict__ B, int64_t count, int64_t per_ind, uint16_t* __restrict__ out,
+                                   int* __restrict__ nanflag) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
         const float x = __ldg(B + i);
+        if (x != x) nanflag[i / per_ind] = 1;
         out[i] = (x != x) ? (uint16_t)m.K : (uint16_t)gbt_rank_of(m.thr_table, m.K, x);
     }
 }
@@ -495,18 +510,21 @@ extern "C" int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_
     // initial labels of the pair as it is: smoother.predict(B) (gnofix.py:80)
     if (gnx_gbt_smooth(m, B_dev, 2 * n_ind, W, nullptr, Y_dev, stream)) return 1;
 
-    // scratch: ranks u16 [2n][W][A] | diff [n][nw] | trk [n][nw] | counter
+    // scratch: ranks u16 [2n][W][A] | diff [n][nw] | trk [n][nw] | counter | NaN flag [n]
     const size_t rb = ((size_t)2 * n_ind * W * A * sizeof(uint16_t) + 255) & ~size_t(255);
     const size_t db = ((size_t)n_ind * nw * 4 + 255) & ~size_t(255);
+    const size_t fb = ((size_t)n_ind * 4 + 255) & ~size_t(255);
     char* scratch = nullptr;
-    GNX_CUDA(cudaMallocAsync((void**)&scratch, rb + 2 * db + 256, st));
+    GNX_CUDA(cudaMallocAsync((void**)&scratch, rb + 2 * db + 256 + fb, st));
     uint16_t* ranks = reinterpret_cast<uint16_t*>(scratch);
     uint32_t* diff = reinterpret_cast<uint32_t*>(scratch + rb);
     uint32_t* trk = reinterpret_cast<uint32_t*>(scratch + rb + db);
     int* counter = reinterpret_cast<int*>(scratch + rb + 2 * db);
-    GNX_CUDA(cudaMemsetAsync(scratch + rb, 0, 2 * db + 256, st));
+    int* nanflag = reinterpret_cast<int*>(scratch + rb + 2 * db + 256);
+    GNX_CUDA(cudaMemsetAsync(scratch + rb, 0, 2 * db + 256 + fb, st));
     const int64_t count = 2 * n_ind * W * A;
-    gnofix_rank_kernel<<<(int)std::min<int64_t>(ceil_div(count, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(m->d, B_dev, count, ranks);
+    gnofix_rank_kernel<<<(int)std::min<int64_t>(ceil_div(count, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(m->d, B_dev, count, (int64_t)2 * W * A,
+                                                                                                     ranks, nanflag);
     if (X_dev)
         gnofix_diff_kernel<<<(unsigned)n_ind, 256, 0, st>>>(X_dev, ldX, C, W, nw, ws, diff);
     else
@@ -537,7 +555,7 @@ extern "C" int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_
     if (!d_stats) GNX_CUDA(cudaMalloc((void**)&d_stats, 4 * sizeof(unsigned long long)));
     GNX_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
     g_gnofix_stats = d_stats;
-    GfArgs g{ranks, diff, trk, hist, Y_dev, tracker_dev, counter, n_ind, W, nw, max_it, teams, team_bytes, (int)leaf_words, d_stats, (em && em[0] == '0') ? 0 : 1, (es && es[0] == '0') ? 0 : 1};
+    GfArgs g{ranks, diff, trk, hist, nanflag, Y_dev, tracker_dev, counter, n_ind, W, nw, max_it, teams, team_bytes, (int)leaf_words, d_stats, (em && em[0] == '0') ? 0 : 1, (es && es[0] == '0') ? 0 : 1};
 #define CALLG(AT)                                                                                                  \
     do {                                                                                                           \
         GNX_CUDA(cudaFuncSetAttribute(gnofix_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -23,6 +23,10 @@ def phase_device(smoother, Xd, ld, C, Bd, max_it=50, want_tracker=False):
     _lib.check(_lib.lib().gnx_gnofix(smoother.model.handle(smoother.S), Xd.data_ptr() if Xd is not None else None, int(ld), int(C),
                                      Bd.data_ptr(), n2 // 2, W, int(max_it), Y.data_ptr(),
                                      trk.data_ptr() if want_tracker else None, st), "gnx_gnofix")
+    refused = int((Y[:, 0] < 0).sum().item()) // 2
+    if refused:
+        raise ValueError("gnofix: the base probabilities of %d individual(s) hold NaN; the rank-form search cannot follow the "
+                         "tree nodes' default children (include/gnx.h, gnx_gnofix) -- clean B first" % refused)
     return Y, trk
 
 

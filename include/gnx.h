@@ -164,8 +164,10 @@ int gnx_svc_kernel_window(const gnx_svc_t* m, int w, const int8_t* X_dev, int64_
  * float32 are updated IN PLACE (tails swapped); Y_dev [2n, W] int32 receives the
  * final labels; tracker_dev [2n, W] int32 (nullable) the gnofix_tracker rows.
  * Needs W >= 2*S (as XGB_Smoother asserts), max_it <= 64, a forest of depth <= 4
- * with <= 65535 distinct thresholds, and finite B (NaN ranks above every threshold
- * instead of following default children).
+ * with <= 65535 distinct thresholds, and B without NaN: a pair whose base
+ * probabilities hold a NaN is REFUSED -- its labels come back as -1, X / B / tracker
+ * untouched -- because the rank form of this kernel cannot follow the default child
+ * of a node the way the smoother kernels do (the Python plugin raises on it).
  * ------------------------------------------------------------------------- */
 int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float* B_dev,
                int64_t n_ind, int W, int max_it, int32_t* Y_dev, int32_t* tracker_dev,

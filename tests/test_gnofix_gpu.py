@@ -120,3 +120,34 @@ def test_gnofix_device_resident_and_B_permuted():
     assert np.array_equal(got[:, 0], want_m) and np.array_equal(got[:, 1], want_p)
     # final labels are the smoother's labels of the final B
     assert np.array_equal(model.smooth.predict(Bd).cpu().numpy(), Y.cpu().numpy())
+
+
+def test_gnofix_refuses_nan_base_probabilities():
+    """A pair whose base probabilities hold a NaN is refused (labels -1 from the C ABI, ValueError from the plugin) rather
+    than phased with NaN semantics that differ from the smoother's default-child rule; the other pairs are unaffected."""
+    import ctypes as C
+    import torch
+    from gnomix_b200 import GBTForest, _lib
+    from oracle import c_oracle as co, np_oracle as npo
+    rng = np.random.default_rng(9)
+    W, A, S, n_ind = 90, 3, 11, 4
+    Cc = W * 23 + 7
+    forest = GBTForest.random(rng, A, S, n_rounds=30, depth=4)
+    X, B = _planted(rng, n_ind, W, A, Cc, n_switch=3)
+    B[2, 40, 1] = np.nan                       # individual 1
+    model = _model(Cc, W, A, S, forest)
+    with pytest.raises(ValueError, match="hold NaN"):
+        model.phase(X, B=B)
+    Xd, Bd = torch.from_numpy(X).cuda(), torch.from_numpy(B).cuda()
+    Y = torch.empty((2 * n_ind, W), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().gnx_gnofix(forest.handle(S), Xd.data_ptr(), Xd.stride(0), Cc, Bd.data_ptr(), n_ind, W, 50, Y.data_ptr(), None, st))
+    Yh = Y.cpu().numpy()
+    assert (Yh[2:4] == -1).all()
+    assert np.array_equal(Xd[2:4].cpu().numpy(), X[2:4])
+    rows_fn = lambda rows: co.gbt_rows(forest, rows)
+    smooth_fn = lambda b: co.gbt_smooth(forest, b, S, want_proba=False)[1]
+    for i in (0, 2, 3):
+        X_m, X_p, Y_m, Y_p, t = npo.gnofix_default(X[2 * i], X[2 * i + 1], B[2 * i:2 * i + 2], S, rows_fn, smooth_fn)
+        assert np.array_equal(Yh[2 * i:2 * i + 2], np.array([Y_m, Y_p]))
+        assert np.array_equal(Xd[2 * i:2 * i + 2].cpu().numpy(), np.array([X_m, X_p]))
