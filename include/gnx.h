@@ -174,8 +174,10 @@ int gnx_gnofix(const gnx_gbt_t* m, int8_t* X_dev, int64_t ldX, int64_t C, float*
                void* stream);
 
 /* profiling counters of the last gnx_gnofix call (synchronises): outer iterations, scans,
- * candidate checks, accepted switches, summed over individuals.  GNX_GNOFIX_MEMO=0 disables
- * the rejected-check memo (cross-check: same results). */
+ * candidate checks, accepted switches, summed over individuals.  Cross-check knobs (same
+ * results): GNX_GNOFIX_MEMO=0 disables the rejected-check memo, GNX_GNOFIX_SPLIT=0 re-smooths
+ * with one thread per row instead of (row, class) chain tasks, GNX_GNOFIX_TEAMS=1..4 bounds the
+ * teams per SM. */
 int gnx_gnofix_last_stats(int64_t* out4);
 
 /* ---------------------------------------------------------------------------

@@ -67,13 +67,20 @@ def _planted(rng, n_ind, W, A, C, n_switch):
     return X, B
 
 
+# memo: "" = default (rejected checks remembered), "0" = every check re-run.  split: "" = default (re-smoothing as (row, class)
+# chain tasks), "0" = one thread per row.  Same results in every combination.
+@pytest.mark.parametrize("split", ["", "0"])
 @pytest.mark.parametrize("memo", ["", "0"])
 @pytest.mark.parametrize("W,A,S,n_ind,seed", [(160, 7, 75, 5, 0), (90, 3, 11, 12, 1), (200, 5, 25, 5, 2), (64, 2, 31, 6, 3)])
-def test_gnofix_matches_oracle(W, A, S, n_ind, seed, memo, monkeypatch):
+def test_gnofix_matches_oracle(W, A, S, n_ind, seed, memo, split, monkeypatch):
     if memo:
         monkeypatch.setenv("GNX_GNOFIX_MEMO", memo)
     else:
         monkeypatch.delenv("GNX_GNOFIX_MEMO", raising=False)
+    if split:
+        monkeypatch.setenv("GNX_GNOFIX_SPLIT", split)
+    else:
+        monkeypatch.delenv("GNX_GNOFIX_SPLIT", raising=False)
     from gnomix_b200 import GBTForest
     from oracle import c_oracle as co, np_oracle as npo
     rng = np.random.default_rng(seed)
