@@ -412,9 +412,12 @@ extern "C" int gnx_infer_host_ex(const gnx_pipeline_t* p, const void* X_host_v, 
     ws.last_frac = 0.0;
     ws.last_h2d = ws.last_d2h = 0;
     int64_t rows_packed = 0, rows_prev = 0;
-    for (int64_t n0 = 0; n0 < N; n0 += chunk, it++) {
+    // ramp: nothing overlaps the pack / H2D of the first chunk, so it is a quarter of a chunk and the second one a half
+    const bool ramp = chunk >= 256 && N > 2 * chunk;
+    int64_t n = 0;
+    for (int64_t n0 = 0; n0 < N; n0 += n, it++) {
         const int s = it & 1, hs = it % kStage;
-        const int64_t n = std::min(chunk, N - n0);
+        n = std::min((ramp && it < 2) ? ((it == 0 ? chunk / 4 : chunk / 2) & ~int64_t(1)) : chunk, N - n0);
         cudaStream_t st = ws.st[s];
         if (adapt) {
             ctl.tick(now_s(), rows_prev);
