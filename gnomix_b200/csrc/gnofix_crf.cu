@@ -19,6 +19,11 @@
 //   K5       marginals of those 4k chains of length S
 //   decide   centre marginals -> accept / reject, tracker bits, rejection memo
 //   gather   the current pair of every individual that switched -> [2k', W, A]; K5; labels scattered back
+// A round takes up to GFC_DEPTH checks of an individual at once: the scan collects its next discontinuities, all of
+// them are scored against the CURRENT pair, and the decision walks them in order -- a rejected check changes nothing,
+// so the ones before the first accepted switch saw exactly the state the one-at-a-time loop would have shown them; the
+// ones behind it are discarded (the scan resumes behind the switch).  Most checks are rejected, so this cuts the number
+// of rounds (each of which pays the latency of a full K5 pass) about threefold.
 // The pair is never swapped in memory: one tracker bit per window says which original haplotype the current "m"
 // row comes from; X and B are permuted once at the end.
 #include <stdlib.h>
@@ -41,14 +46,20 @@ struct GfcState {
     uint32_t* hist;         // [n][max_it][nw] tracker at the start of every outer iteration
     int* it;                // [n] outer iterations started
     int* wcur;              // [n] next window to scan
-    int* wsel;              // [n] window checked this round
+    int* cbase;             // [n] first entry of the individual's checks of this round in cand_w / cand_i
+    int* ncand;             // [n] number of them (<= GFC_DEPTH)
+    unsigned char* ended;   // [n] the scan of this round reached the last window
     unsigned char* done;    // [n]
-    int* act;               // compact list: individuals with a check this round
+    int* act;               // compact list: individuals with checks this round
+    int* cand_w;            // compact list: window of every check of this round
+    int* cand_i;            // ... and its individual
     int* sw;                // compact list: individuals that switched this round
-    int* counts;            // [0] |act|, [1] |sw|
+    int* counts;            // [0] |act|, [1] |sw|, [2] checks scored this round, [3] checks the one-at-a-time loop would have run
     int64_t n;
     int W, A, S, nw, max_it, memo;
 };
+
+constexpr int GFC_DEPTH = 4;   // checks of one individual scored per round
 
 __device__ __forceinline__ uint32_t gfc_bit(const uint32_t* v, int j) { return (v[j >> 5] >> (j & 31)) & 1u; }
 
@@ -65,17 +76,34 @@ __global__ void gfc_scan_kernel(GfcState g) {
     uint32_t* hist = g.hist + i * (int64_t)g.max_it * nw;
     int wcur = g.wcur[i], it = g.it[i];
     for (;;) {
-        int found = W;
-        for (int base = wcur; base < W && found == W; base += 32) {
+        // the next (up to GFC_DEPTH) windows with a discontinuity in either haplotype (gnofix.py:116-118) and no
+        // remembered rejection
+        int cw[GFC_DEPTH];
+        int c = 0;
+        bool ended = true;
+        for (int base = wcur; base < W; base += 32) {
             const int ww = base + lane;
             const bool hit = ww < W && (y0[ww] != y0[ww - 1] || y1[ww] != y1[ww - 1]) && !gfc_bit(rej, ww);
-            const unsigned b = __ballot_sync(0xffffffffu, hit);
-            if (b) found = base + __ffs(b) - 1;
+            unsigned b = __ballot_sync(0xffffffffu, hit);
+            while (b && c < GFC_DEPTH) {
+                cw[c++] = base + __ffs(b) - 1;
+                b &= b - 1;
+            }
+            if (c == GFC_DEPTH) {
+                ended = false;   // (windows may remain behind the last one taken)
+                break;
+            }
         }
-        if (found < W) {   // gnofix.py:116-118: a discontinuity in either haplotype
+        if (c > 0) {
             if (lane == 0) {
-                g.wsel[i] = found;
-                g.wcur[i] = found + 1;
+                const int cb = atomicAdd(&g.counts[2], c);
+                for (int j = 0; j < c; j++) {
+                    g.cand_w[cb + j] = cw[j];
+                    g.cand_i[cb + j] = (int)i;
+                }
+                g.cbase[i] = cb;
+                g.ncand[i] = c;
+                g.ended[i] = ended ? 1 : 0;
                 g.it[i] = it;
                 g.act[atomicAdd(&g.counts[0], 1)] = (int)i;
             }
@@ -92,7 +120,7 @@ __global__ void gfc_scan_kernel(GfcState g) {
         if (stop) {
             if (lane == 0) {
                 g.done[i] = 1;
-                g.wsel[i] = -1;
+                g.ncand[i] = 0;
                 g.it[i] = it;
             }
             return;
@@ -104,15 +132,15 @@ __global__ void gfc_scan_kernel(GfcState g) {
 }
 
 // rows[(4k + r)][s][:]: r = 0, 1 the pair as it is, r = 2, 3 with the tails swapped at w (gnofix.py:140-157)
-__global__ void gfc_build_kernel(GfcState g, double* __restrict__ rows, int nact) {
+__global__ void gfc_build_kernel(GfcState g, double* __restrict__ rows, int ncand) {
     const int S = g.S, A = g.A, W = g.W;
-    const int64_t total = (int64_t)nact * 4 * S;
+    const int64_t total = (int64_t)ncand * 4 * S;
     const int half = (S - 1) / 2;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(idx / (4 * S)), rem = (int)(idx - (int64_t)k * 4 * S);
         const int r = rem / S, s = rem - r * S;
-        const int64_t i = g.act[k];
-        const int w = g.wsel[i];
+        const int64_t i = g.cand_i[k];
+        const int w = g.cand_w[k];
         const int center = min(max(w, half), W - S + half);
         const int j = center - half + s;
         const int h = r & 1;
@@ -124,35 +152,46 @@ __global__ void gfc_build_kernel(GfcState g, double* __restrict__ rows, int nact
     }
 }
 
+// one thread per individual with checks this round: its checks in scan order, up to the first accepted switch
 __global__ void gfc_decide_kernel(GfcState g, const double* __restrict__ marg, int L, int nact) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nact) return;
     const int S = g.S, W = g.W, nw = g.nw;
     const int64_t i = g.act[k];
-    const int w = g.wsel[i];
     const int c = (S - 1) / 2;
-    double p[4];
-    for (int r = 0; r < 4; r++) {
-        const double* mrow = marg + (((int64_t)4 * k + r) * S + c) * L;
-        double best = mrow[0];
-        for (int y = 1; y < L; y++) best = (mrow[y] > best) ? mrow[y] : best;
-        p[r] = best;
-    }
-    const double p_orig = (p[1] > p[0]) ? p[1] : p[0], p_sw = (p[3] > p[2]) ? p[3] : p[2];
     uint32_t* trk = g.trk + i * nw;
     uint32_t* rej = g.rej + i * nw;
-    if (!(p_sw * 0.5 > p_orig * 0.5)) {   // gnofix.py:171, prior_switch_prob = 0.5
-        if (g.memo) rej[w >> 5] |= 1u << (w & 31);
+    const int cb = g.cbase[i], nc = g.ncand[i];
+    for (int j = 0; j < nc; j++) {
+        const int w = g.cand_w[cb + j];
+        double p[4];
+        for (int r = 0; r < 4; r++) {
+            const double* mrow = marg + (((int64_t)4 * (cb + j) + r) * S + c) * L;
+            double best = mrow[0];
+            for (int y = 1; y < L; y++) best = (mrow[y] > best) ? mrow[y] : best;
+            p[r] = best;
+        }
+        const double p_orig = (p[1] > p[0]) ? p[1] : p[0], p_sw = (p[3] > p[2]) ? p[3] : p[2];
+        if (!(p_sw * 0.5 > p_orig * 0.5)) {   // gnofix.py:171, prior_switch_prob = 0.5
+            if (g.memo) rej[w >> 5] |= 1u << (w & 31);
+            continue;
+        }
+        // accepted: the checks behind it were scored against a pair that no longer exists -- the scan resumes at w + 1
+        for (int ww = max(1, w - S); ww <= min(W - 1, w + S); ww++) rej[ww >> 5] &= ~(1u << (ww & 31));
+        for (int q = w >> 5; q < nw; q++) {
+            uint32_t mask = 0xffffffffu;
+            if (q == (w >> 5)) mask <<= (w & 31);
+            if (q == nw - 1 && (W & 31)) mask &= (1u << (W & 31)) - 1u;
+            trk[q] ^= mask;
+        }
+        g.wcur[i] = w + 1;
+        g.sw[atomicAdd(&g.counts[1], 1)] = (int)i;
+        atomicAdd(&g.counts[3], j + 1);
         return;
     }
-    for (int ww = max(1, w - S); ww <= min(W - 1, w + S); ww++) rej[ww >> 5] &= ~(1u << (ww & 31));
-    for (int q = w >> 5; q < nw; q++) {
-        uint32_t mask = 0xffffffffu;
-        if (q == (w >> 5)) mask <<= (w & 31);
-        if (q == nw - 1 && (W & 31)) mask &= (1u << (W & 31)) - 1u;
-        trk[q] ^= mask;
-    }
-    g.sw[atomicAdd(&g.counts[1], 1)] = (int)i;
+    // every check of the round rejected: resume behind the last one (or end the outer iteration)
+    g.wcur[i] = g.ended[i] ? W : g.cand_w[cb + nc - 1] + 1;
+    atomicAdd(&g.counts[3], nc);
 }
 
 // the current pair of switched individuals sw[off .. off + cnt): pairs[(2k + h)][j][:] = B[2i + (h ^ trk[j])][j][:]
@@ -184,7 +223,8 @@ __global__ void gfc_init_kernel(GfcState g) {
     if (i >= g.n) return;
     g.it[i] = 0;
     g.wcur[i] = 1;
-    g.wsel[i] = -1;
+    g.ncand[i] = 0;
+    g.ended[i] = 0;
     g.done[i] = 0;
 }
 
@@ -262,8 +302,9 @@ extern "C" int gnx_gnofix_crf(const gnx_crf_t* m, int S, int8_t* X_dev, int64_t 
 
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
     const size_t b_bits = al((size_t)n_ind * nw * 4), b_hist = al((size_t)n_ind * max_it * nw * 4), b_int = al((size_t)n_ind * 4);
-    const size_t b_rows = al((size_t)n_ind * 4 * S * A * 8), b_pairs = al((size_t)cap * 2 * W * A * 8), b_lab = al((size_t)cap * 2 * W * 4);
-    const size_t total = 3 * b_bits + b_hist + 5 * b_int + al((size_t)n_ind) + 256 + 2 * b_rows + 2 * b_pairs + b_lab;
+    const size_t b_cand = al((size_t)n_ind * GFC_DEPTH * 4), b_byte = al((size_t)n_ind);
+    const size_t b_rows = al((size_t)n_ind * GFC_DEPTH * 4 * S * A * 8), b_pairs = al((size_t)cap * 2 * W * A * 8), b_lab = al((size_t)cap * 2 * W * 4);
+    const size_t total = 3 * b_bits + b_hist + 6 * b_int + 2 * b_cand + 2 * b_byte + 256 + 2 * b_rows + 2 * b_pairs + b_lab;
     char* scratch = nullptr;
     GNX_CUDA(cudaMallocAsync((void**)&scratch, total, st));
     char* q = scratch;
@@ -278,10 +319,14 @@ extern "C" int gnx_gnofix_crf(const gnx_crf_t* m, int S, int8_t* X_dev, int64_t 
     g.hist = reinterpret_cast<uint32_t*>(take(b_hist));
     g.it = reinterpret_cast<int*>(take(b_int));
     g.wcur = reinterpret_cast<int*>(take(b_int));
-    g.wsel = reinterpret_cast<int*>(take(b_int));
+    g.cbase = reinterpret_cast<int*>(take(b_int));
+    g.ncand = reinterpret_cast<int*>(take(b_int));
     g.act = reinterpret_cast<int*>(take(b_int));
     g.sw = reinterpret_cast<int*>(take(b_int));
-    g.done = reinterpret_cast<unsigned char*>(take(al((size_t)n_ind)));
+    g.cand_w = reinterpret_cast<int*>(take(b_cand));
+    g.cand_i = reinterpret_cast<int*>(take(b_cand));
+    g.ended = reinterpret_cast<unsigned char*>(take(b_byte));
+    g.done = reinterpret_cast<unsigned char*>(take(b_byte));
     g.counts = reinterpret_cast<int*>(take(256));
     double* rows = reinterpret_cast<double*>(take(b_rows));
     double* marg_rows = reinterpret_cast<double*>(take(b_rows));
@@ -300,7 +345,7 @@ extern "C" int gnx_gnofix_crf(const gnx_crf_t* m, int S, int8_t* X_dev, int64_t 
         cudaFreeAsync(scratch, st);
         return code;
     };
-    if (cudaMallocHost((void**)&h_counts, 2 * sizeof(int)) != cudaSuccess) {
+    if (cudaMallocHost((void**)&h_counts, 4 * sizeof(int)) != cudaSuccess) {
         set_error("gnx_gnofix_crf: pinned allocation failed");
         return fail(1);
     }
@@ -331,24 +376,24 @@ extern "C" int gnx_gnofix_crf(const gnx_crf_t* m, int S, int8_t* X_dev, int64_t 
     }
     int64_t rounds = 0, checks = 0, accepts = 0;
     for (;;) {
-        GFC_CUDA(cudaMemsetAsync(g.counts, 0, 2 * sizeof(int), st));
+        GFC_CUDA(cudaMemsetAsync(g.counts, 0, 4 * sizeof(int), st));
         gfc_scan_kernel<<<(unsigned)ceil_div(n_ind * 32, 256), 256, 0, st>>>(g);
         GFC_CUDA(cudaGetLastError());
-        GFC_CUDA(cudaMemcpyAsync(h_counts, g.counts, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GFC_CUDA(cudaMemcpyAsync(h_counts, g.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         GFC_CUDA(cudaStreamSynchronize(st));
-        const int nact = h_counts[0];
+        const int nact = h_counts[0], ncand = h_counts[2];
         if (nact == 0) break;   // every individual is done
         rounds++;
-        checks += nact;
-        gfc_build_kernel<<<(unsigned)std::min<int64_t>(ceil_div((int64_t)nact * 4 * S, 256), (int64_t)sm_count() * 8), 256, 0, st>>>(g, rows, nact);
+        gfc_build_kernel<<<(unsigned)std::min<int64_t>(ceil_div((int64_t)ncand * 4 * S, 256), (int64_t)sm_count() * 8), 256, 0, st>>>(g, rows, ncand);
         GFC_CUDA(cudaGetLastError());
-        rc = gnx_crf_smooth(m, rows, (int64_t)4 * nact, S, marg_rows, nullptr, stream);
+        rc = gnx_crf_smooth(m, rows, (int64_t)4 * ncand, S, marg_rows, nullptr, stream);
         if (rc) return fail(rc);
         gfc_decide_kernel<<<(unsigned)ceil_div(nact, 128), 128, 0, st>>>(g, marg_rows, L, nact);
         GFC_CUDA(cudaGetLastError());
-        GFC_CUDA(cudaMemcpyAsync(h_counts + 1, g.counts + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GFC_CUDA(cudaMemcpyAsync(h_counts, g.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         GFC_CUDA(cudaStreamSynchronize(st));
         const int nsw = h_counts[1];
+        checks += h_counts[3];
         accepts += nsw;
         // full re-smoothing of the pairs that switched (Smoother.predict, gnofix.py:190)
         for (int off = 0; off < nsw; off += (int)cap) {
