@@ -23,9 +23,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
+#include "host_pack.h"
 
 namespace gnx {
 
@@ -591,40 +593,64 @@ int gnx_svc_model_create(gnx_svc_t** out, int A, int64_t C, int64_t M, int64_t c
     std::vector<uint32_t> planes;
     std::vector<double> coef;
     std::vector<size_t> plane_off(W), coef_off(W);
-    int64_t sv_off = 0, coef_in = 0;
+    int64_t coef_in = 0;
     int max_nsv = 0;
-    for (int64_t w = 0; w < W; w++) {
-        int nsv = 0;
-        for (int c = 0; c < A; c++) {
-            GNX_REQUIRE(n_support[w * A + c] >= 0, "gnx_svc_model_create: negative n_support");
-            nsv += n_support[w * A + c];
-        }
-        const int len = (int)((w == W - 1) ? (M_ + rem) : M_);
-        const int nw = (len + 31) / 32;
-        SvcWin& sw = m->win[w];
-        sw.lo = (w == W - 1) ? (C + 2 * ctx - (M_ + rem)) : w * M;
-        sw.len = len; sw.nw = nw; sw.nwp = nw | 1; sw.nsv = nsv;
-        plane_off[w] = planes.size();
-        planes.resize(planes.size() + (size_t)nsv * 2 * nw, 0u);
-        uint32_t* pw = planes.data() + plane_off[w];
-        for (int s = 0; s < nsv; s++) {
-            const int8_t* row = sv + sv_off + (int64_t)s * len;
-            for (int p = 0; p < len; p++) {
-                const int v = row[p];
-                if (v < 0 || v > 3) {
+    std::vector<int64_t> sv_offs(W);
+    {
+        int64_t sv_off = 0;
+        size_t pl = 0;
+        for (int64_t w = 0; w < W; w++) {
+            int nsv = 0;
+            for (int c = 0; c < A; c++) {
+                if (n_support[w * A + c] < 0) {
                     delete m;
-                    set_error("gnx_svc_model_create: support vector value %d outside 0..3 (window %lld)", v, (long long)w);
+                    set_error("gnx_svc_model_create: negative n_support");
                     return 2;
                 }
-                if (v & 1) pw[((size_t)s * 2 + 0) * nw + (p >> 5)] |= 1u << (p & 31);
-                if (v & 2) pw[((size_t)s * 2 + 1) * nw + (p >> 5)] |= 1u << (p & 31);
+                nsv += n_support[w * A + c];
+            }
+            const int len = (int)((w == W - 1) ? (M_ + rem) : M_);
+            const int nw = (len + 31) / 32;
+            SvcWin& sw = m->win[w];
+            sw.lo = (w == W - 1) ? (C + 2 * ctx - (M_ + rem)) : w * M;
+            sw.len = len; sw.nw = nw; sw.nwp = nw | 1; sw.nsv = nsv;
+            plane_off[w] = pl;
+            pl += (size_t)nsv * 2 * nw;
+            sv_offs[w] = sv_off;
+            sv_off += (int64_t)nsv * len;
+            coef_off[w] = coef.size();
+            coef.insert(coef.end(), dual_coef + coef_in, dual_coef + coef_in + (int64_t)(A - 1) * nsv);
+            coef_in += (int64_t)(A - 1) * nsv;
+            max_nsv = std::max(max_nsv, nsv);
+        }
+        planes.assign(pl, 0u);
+    }
+    // bit planes of the support vectors, windows in parallel on the host worker pool (1.7e9 values for chr1 with 700
+    // vectors per window: 8.7 s as a scalar loop on one thread), each row through the vector pack of host_pack.cpp
+    std::atomic<long long> bad_window{-1};
+    parallel_for(W, 0, [&](int64_t w) {
+        const SvcWin& sw = m->win[w];
+        const int len = sw.len, nw = sw.nw, groups = (len + 63) / 64;
+        std::vector<uint64_t> tmp((size_t)2 * groups);
+        uint32_t* pw = planes.data() + plane_off[w];
+        for (int s = 0; s < sw.nsv; s++) {
+            if (pack_row_best(sv + sv_offs[w] + (int64_t)s * len, len, tmp.data(), groups)) {
+                bad_window.store((long long)w);
+                return;
+            }
+            uint32_t* p0 = pw + ((size_t)s * 2 + 0) * nw;
+            uint32_t* p1 = pw + ((size_t)s * 2 + 1) * nw;
+            for (int j = 0; j < nw; j++) {
+                p0[j] = (uint32_t)(tmp[2 * (j >> 1)] >> (32 * (j & 1)));
+                p1[j] = (uint32_t)(tmp[2 * (j >> 1) + 1] >> (32 * (j & 1)));
             }
         }
-        sv_off += (int64_t)nsv * len;
-        coef_off[w] = coef.size();
-        coef.insert(coef.end(), dual_coef + coef_in, dual_coef + coef_in + (int64_t)(A - 1) * nsv);
-        coef_in += (int64_t)(A - 1) * nsv;
-        max_nsv = std::max(max_nsv, nsv);
+    });
+    if (bad_window.load() >= 0) {
+        const long long bw = bad_window.load();
+        delete m;
+        set_error("gnx_svc_model_create: a support vector value outside 0..3 (window %lld)", bw);
+        return 2;
     }
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_pl = 0, o_cf = al(planes.size() * 4), o_ns = o_cf + al(coef.size() * 8), o_ic = o_ns + al((size_t)W * A * 4),
