@@ -209,3 +209,41 @@ def test_mode_filter_restatement_and_plugin_against_reference():
         y, size, A = d["y_" + t], int(d["size_" + t]), int(d["A_" + t])
         assert np.array_equal(np.stack([npo.mode_filter(r, size) for r in y]), d["out_" + t]), t
         assert np.array_equal(mode_filter_device(torch.from_numpy(y.astype(np.int32)), size, A).numpy(), d["out_" + t]), t
+
+
+def test_gnofix_crf_extension_oracle_is_self_consistent():
+    """The CRF + Gnofix extension has no reference behaviour (src/model.py:194): its checker is the pinned gnofix control
+    flow with the oracle's CRF plugged in.  Here: the NumPy and the C restatement of the CRF give the same phasing, the
+    scorer is the centre marginal of the scope run as its own chain, and planted switch errors get undone."""
+    from oracle import c_oracle as co, np_oracle as npo
+    rng = np.random.default_rng(4)
+    W, A, S = 60, 3, 9
+    C = W * 7 + 2
+    sw = np.eye(A) * 4.0 + rng.normal(0, 0.3, (A, A))
+    tw = np.eye(A) * 2.0 + rng.normal(0, 0.3, (A, A))
+    anc = np.zeros((2, W), dtype=int)
+    anc[0, 25:] = 1
+    anc[1, :40] = 2
+    b = 0.05 + rng.random((2, W, A)) * 0.2
+    for h in range(2):
+        b[h, np.arange(W), anc[h]] += 0.7
+    b /= b.sum(-1, keepdims=True)
+    clean = b.copy()
+    b[:, 30:] = b[::-1, 30:].copy()            # one planted switch error at window 30
+    X = rng.integers(0, 2, size=(2, C)).astype(np.int8)
+    r_np = npo.gnofix_crf_extension(X[0], X[1], b, S, sw, tw)
+    r_c = npo.gnofix_crf_extension(X[0], X[1], b, S, sw, tw, crf_smooth_fn=co.crf_smooth)
+    for a_, c_ in zip(r_np, r_c):
+        assert np.array_equal(a_, c_)
+    X_m, X_p, Y_m, Y_p, trk = r_np
+    assert (trk[0][1:] != trk[0][:-1]).sum() >= 1                       # it switched
+    # the scorer: centre marginal of a scope as its own chain
+    rows = b[0, 10:10 + S].reshape(1, -1)
+    marg, _ = npo.crf_smooth(rows.reshape(1, S, A), sw, tw)
+    assert marg.shape == (1, S, A) and abs(marg[0, (S - 1) // 2].sum() - 1.0) < 1e-12
+    # after phasing, each haplotype's labels follow one of the clean tracks again (up to which row is called m)
+    clean_lab = npo.crf_smooth(clean, sw, tw)[1]
+    got = np.array([Y_m, Y_p])
+    same = (got == clean_lab).mean()
+    swapped = (got == clean_lab[::-1]).mean()
+    assert max(same, swapped) > 0.9
