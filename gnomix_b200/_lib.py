@@ -81,7 +81,7 @@ EXPORTS = tuple(_SIGS)
 class Pipeline(C.Structure):
     """gnx_pipeline_t (include/gnx.h)."""
     _fields_ = [("lr", c_vp), ("svc", c_vp), ("gbt", c_vp), ("crf", c_vp), ("cal", c_vp),
-                ("phase", C.c_int), ("max_it", C.c_int), ("x_packed", C.c_int)]
+                ("phase", C.c_int), ("max_it", C.c_int), ("x_packed", C.c_int), ("crf_phase_S", C.c_int)]
 
 
 def lib():

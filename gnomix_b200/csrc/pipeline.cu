@@ -266,7 +266,8 @@ extern "C" int gnx_infer_host_ex(const gnx_pipeline_t* p, const void* X_host_v, 
     GNX_REQUIRE(p != nullptr, "gnx_infer_host_ex: NULL pipeline");
     GNX_REQUIRE((p->lr != nullptr) != (p->svc != nullptr), "gnx_infer_host_ex: exactly one base model (lr or svc) is needed");
     GNX_REQUIRE((p->gbt != nullptr) != (p->crf != nullptr), "gnx_infer_host_ex: exactly one smoother (gbt or crf) is needed");
-    GNX_REQUIRE(!p->phase || p->gbt, "gnx_infer_host_ex: Gnofix needs the tree smoother (src/model.py:194)");
+    GNX_REQUIRE(!p->phase || p->gbt || (p->crf && p->crf_phase_S > 0),
+                "gnx_infer_host_ex: Gnofix needs the tree smoother (src/model.py:194); the CRF extension is opted into with crf_phase_S");
     int64_t C = 0;
     int W = 0, A = 0;
     if (p->lr) { C = p->lr->d.C; W = p->lr->d.W; A = p->lr->d.A; }
@@ -477,8 +478,15 @@ extern "C" int gnx_infer_host_ex(const gnx_pipeline_t* p, const void* X_host_v, 
         if (p->phase) {
             // Gnomix.phase (src/model.py:188-214): X and B swapped in place, labels from gnofix; the probabilities the
             // driver writes are those of the phased haplotypes run through the model again (gnomix.py:72)
-            float* b32 = const_cast<float*>(smoother_input(s, n, st));
-            if (gnx_gnofix(p->gbt, ws.X(s), pitch, C, b32, n / 2, W, p->max_it > 0 ? p->max_it : 50, lab_dev, nullptr, st)) return 1;
+            if (p->gbt) {
+                float* b32 = const_cast<float*>(smoother_input(s, n, st));
+                if (gnx_gnofix(p->gbt, ws.X(s), pitch, C, b32, n / 2, W, p->max_it > 0 ? p->max_it : 50, lab_dev, nullptr, st)) return 1;
+            } else {
+                // the CRF + Gnofix extension (no reference behaviour): float64 base probabilities, rounds with host syncs
+                if (gnx_gnofix_crf(p->crf, p->crf_phase_S, ws.X(s), pitch, C, static_cast<double*>(ws.dev[D_B][s]), n / 2, W,
+                                   p->max_it > 0 ? p->max_it : 50, lab_dev, nullptr, st))
+                    return 1;
+            }
             labels_done = true;
             if (X_phased_host) {
                 GNX_CUDA(cudaMemcpy2DAsync(xph_direct ? (void*)(X_phased_host + n0 * C) : ws.host[H_X][s], (size_t)C, ws.X(s), (size_t)pitch,

@@ -181,7 +181,7 @@ class Gnomix:
         return phase_all(self, X, B=B, verbose=verbose, want_tracker=want_tracker)
 
     # -- host-buffer fast path (include/gnx.h gnx_infer_host_ex) ------------------
-    def predict_host(self, X, want_proba=False, chunk_haps=0, phase=False, want_phased=False):
+    def predict_host(self, X, want_proba=False, chunk_haps=0, phase=False, want_phased=False, crf_extension=False):
         """One call from a HOST haplotype matrix to labels: chunks stream through Base -> [Gnofix] -> Smoother ->
         [Calibrator] on two device slots with the copies overlapped (gnomix.py:48-72 as one pipeline).
         X: numpy / torch-CPU int8 [N, >=C] (pageable or pinned), or a `gnomix_b200.io.PackedHaplotypes`
@@ -220,9 +220,13 @@ class Gnomix:
         if getattr(self.smooth, "mode_filter", 0) not in (0, 1, False, True, None):
             raise NotImplementedError("predict_host does not apply smooth.mode_filter; use predict()")
         if phase:
-            assert getattr(self.smooth, "gnofix", False) and pipe.gbt, \
+            # the reference's refusal (src/model.py:194) stands unless the CRF + Gnofix extension is asked for by name
+            ext = bool(crf_extension) and bool(pipe.crf)
+            assert (getattr(self.smooth, "gnofix", False) and pipe.gbt) or ext, \
                 "Type of Smoother ({}) does not currently support re-phasing".format(self.smooth)
             pipe.phase = 1
+            if ext:
+                pipe.crf_phase_S = int(self.smooth.S)
         if isinstance(X, PackedHaplotypes):
             N, Cx, ld, xp = X.N, X.C, X.pitch_words, X.words.ctypes.data
             pipe.x_packed = 1

@@ -253,6 +253,8 @@ typedef struct gnx_pipeline {
     int phase;
     int max_it;
     int x_packed;
+    int crf_phase_S;   /* > 0 with phase and crf: the CRF + Gnofix EXTENSION (gnx_gnofix_crf, no reference behaviour) with
+                          this smoother width; 0 keeps the reference's refusal (src/model.py:194) */
 } gnx_pipeline_t;
 int gnx_infer_host_ex(const gnx_pipeline_t* p, const void* X_host, int64_t N, int64_t ldX, void* proba_host,
                       int32_t* label_host, int8_t* X_phased_host, int64_t chunk_haps);

@@ -93,3 +93,29 @@ def test_gnofix_crf_device_tensors_and_numpy_oracle():
         for h in range(2):
             exp = np.stack([B[2 * i + t[h][j], j] for j in range(W)])
             assert np.array_equal(Bd[2 * i + h].cpu().numpy(), exp)
+
+
+def test_crf_phase_pipeline_equals_phase_then_predict():
+    """gnx_infer_host_ex with phase and a CRF smoother (crf_phase_S): the extension inside the one-call host pipeline ==
+    Gnomix.phase(crf_extension=True) followed by predict_proba on the phased haplotypes; refused without the opt-in."""
+    from gnomix_b200 import Gnomix, synth
+    from gnomix_b200.smooth import CRF_Smoother
+    from tests import util
+    rng = np.random.default_rng(31)
+    C, M, A, S = 24_000, 400, 4, 9
+    model = Gnomix(C, M, A, S)
+    coefs, icpts, _ = util.random_lr(rng, C, M, A)
+    model.base.set_window_weights(coefs, icpts)
+    model.smooth = CRF_Smoother(n_windows=C // M, num_ancestry=A, smooth_window_size=S)
+    model.smooth.model = _crf(rng, A)
+    freqs = synth.population_frequencies(rng, C, A, fst=0.3)
+    fx, fpop = synth.founders(rng, freqs, per_pop=6)
+    X, _ = synth.admix_host(rng, fx, fpop, 41, morgans=1.0)     # odd: the trailing haplotype is dropped
+    with pytest.raises(AssertionError):
+        model.predict_host(X, phase=True)
+    Xp_ref, y_ref = model.phase(X, crf_extension=True)
+    p_ref = model.predict_proba(Xp_ref.astype(np.int8))
+    y, p, Xp = model.predict_host(X, want_proba=True, phase=True, want_phased=True, chunk_haps=16, crf_extension=True)
+    assert y.shape == (40, model.W) and np.array_equal(y, y_ref)
+    assert np.array_equal(Xp, Xp_ref)
+    assert np.array_equal(np.ascontiguousarray(p).view(np.uint64), np.ascontiguousarray(p_ref).view(np.uint64))
